@@ -1,0 +1,51 @@
+# Top-level build: libraytrace_b200.so (C ABI, include/rt_cuda.h) for sm_100a.
+#
+#   make            build the product library in-tree (ray_tracing_b200/)
+#   make oracle     build the test-only checkers (oracle/)
+#   make harness    build the headless C harness (tools/rt_headless)
+NVCC      ?= /usr/local/cuda/bin/nvcc
+CC        ?= gcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+SRC       := ray_tracing_b200/csrc
+OBJ       := build/obj
+LIB       := ray_tracing_b200/libraytrace_b200.so
+NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Iinclude -I$(SRC) -Xcompiler -fPIC -Xcompiler -ffp-contract=off \
+             --expt-relaxed-constexpr -Xptxas -v
+# host C: the reference's own flags matter for float parity (no contraction)
+CFLAGS    := -std=c11 -O2 -fPIC -ffp-contract=off -Wall -Wextra -Iinclude -I$(SRC)
+
+HOST_OBJS := $(OBJ)/scene_parse.o $(OBJ)/camera_host.o $(OBJ)/scene_pack.o
+CUDA_OBJS := $(OBJ)/rt_api.o $(OBJ)/rt_lbvh.o $(OBJ)/rt_render_exact.o $(OBJ)/rt_render_fast.o
+DEVICE_HDRS := $(SRC)/rt_device.cuh $(SRC)/rt_params.h $(SRC)/rt_host.h $(SRC)/rt_lbvh.h include/rt_cuda.h
+
+.PHONY: all oracle harness clean
+all: $(LIB)
+
+$(OBJ)/%.o: $(SRC)/%.c include/rt_cuda.h $(SRC)/rt_host.h
+	@mkdir -p $(OBJ)
+	$(CC) $(CFLAGS) -c -o $@ $<
+
+$(OBJ)/rt_api.o: $(SRC)/rt_api.cu $(DEVICE_HDRS)
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -c -o $@ $< 2> $(OBJ)/rt_api.ptxas.log || (cat $(OBJ)/rt_api.ptxas.log; false)
+$(OBJ)/rt_lbvh.o: $(SRC)/rt_lbvh.cu $(DEVICE_HDRS)
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -c -o $@ $< 2> $(OBJ)/rt_lbvh.ptxas.log || (cat $(OBJ)/rt_lbvh.ptxas.log; false)
+# the render kernels twice: bit-exact (no FMA contraction) and fast
+$(OBJ)/rt_render_exact.o: $(SRC)/rt_render.cu $(DEVICE_HDRS)
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -DRT_NS=rt_exact -fmad=false -prec-div=true -prec-sqrt=true -ftz=false -c -o $@ $< \
+	    2> $(OBJ)/rt_render_exact.ptxas.log || (cat $(OBJ)/rt_render_exact.ptxas.log; false)
+$(OBJ)/rt_render_fast.o: $(SRC)/rt_render.cu $(DEVICE_HDRS)
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -DRT_NS=rt_fast -fmad=true -c -o $@ $< \
+	    2> $(OBJ)/rt_render_fast.ptxas.log || (cat $(OBJ)/rt_render_fast.ptxas.log; false)
+
+$(LIB): $(HOST_OBJS) $(CUDA_OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $^ -lcudart_static -lm -lpthread -ldl -lrt
+
+oracle:
+	$(MAKE) -C oracle all
+
+clean:
+	rm -rf build $(LIB)

@@ -1,0 +1,243 @@
+/*
+ * rt_cuda.h -- C ABI of the B200-native render path for cozis/ray_tracing.
+ *
+ * This library replaces, behind plain C entry points, the reference's
+ *   worker()/render_column()/pixel()        src/main.c:131-414
+ *   trace_ray() + intersectors              src/scene.c:10-190
+ *   ray_through_screen_at()                 src/camera.c:95-125
+ *   sample_cubemap()                        src/gpu_and_windowing.c:42-112
+ *   the accumulate/resolve of update_frame  src/main.c:387-396, 467-477
+ * and keeps the reference's host-side API for the callers either side of it:
+ *   parse_scene_file()                      src/scene.h:47, scene.c:611-624
+ *   move_camera/rotate_camera/get_camera_pos src/camera.h:25-29
+ * There is no plugin/FFI layer in the reference; the seam is those C functions
+ * (SURVEY.md section 8(b)).  INTEGRATION.md shows the lines a maintainer changes
+ * in main.c.
+ *
+ * Conventions: every call returns RT_OK (0) or a negative RT_ERR_* code and
+ * never aborts; rt_cuda_last_error() gives the message.  All structs are POD.
+ * Calls are made from one host thread.  There is NO CPU fallback: without a
+ * CUDA device every rendering call fails with RT_ERR_NO_DEVICE.
+ */
+#ifndef RT_CUDA_H
+#define RT_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include <stdbool.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------- */
+/* Types, layout-identical to the reference's (sizes probed in SURVEY.md R11) */
+/* ------------------------------------------------------------------------- */
+
+#ifdef RT_CUDA_REFERENCE_TYPES
+/* Building inside the reference tree: vector.h / scene.h /
+ * gpu_and_windowing.h were included first; reuse their types. */
+typedef Vector3  RtVector3;
+typedef Material RtMaterial;
+typedef Object   RtObject;
+typedef Scene    RtScene;
+typedef Cubemap  RtCubemap;
+#define RT_MAX_OBJECTS MAX_OBJECTS
+#else
+
+#define RT_MAX_OBJECTS 1024                 /* scene.h:3 */
+
+typedef struct { float x, y, z; } RtVector3; /* vector.h:32-36, 12 B */
+
+typedef struct {                            /* scene.h:5-12, 40 B */
+	RtVector3 albedo;
+	float     roughness;
+	float     reflectance;
+	float     metallic;
+	float     emission_power;
+	RtVector3 emission_color;
+} RtMaterial;
+
+typedef enum { RT_OBJECT_CUBE = 0, RT_OBJECT_SPHERE = 1 } RtObjectType;   /* scene.h:19-22 */
+
+typedef struct {                            /* scene.h:24-31, 68 B */
+	RtObjectType type;
+	union {
+		struct { RtVector3 center; float radius; } sphere;   /* vector.h:58-61 */
+		struct { RtVector3 origin; RtVector3 size; } cube;    /* scene.h:14-17 */
+	};
+	RtMaterial material;
+} RtObject;
+
+typedef struct {                            /* scene.h:33-36, 69 636 B */
+	RtObject objects[RT_MAX_OBJECTS];
+	int      num_objects;
+} RtScene;
+
+typedef struct {                            /* gpu_and_windowing.h:4-7 */
+	uint8_t *data[6];                       /* CubeFace order (gpu_and_windowing.h:9-16) */
+	int w, h, chan;
+} RtCubemap;
+#endif
+
+enum { RT_CF_FRONT = 0, RT_CF_BACK, RT_CF_LEFT, RT_CF_RIGHT, RT_CF_TOP, RT_CF_BOTTOM };
+
+/* The reference keeps the pose in file statics (camera.c:23-35); this is the
+ * snapshot handed to the renderer. */
+typedef struct {
+	RtVector3 pos;
+	RtVector3 front;                        /* not normalised by the caller */
+	RtVector3 up;
+	float     fov;                          /* passed to tan() as radians, camera.c:107 */
+} RtCamera;
+
+typedef enum { RT_UP = 0, RT_DOWN, RT_LEFT, RT_RIGHT } RtDirection;   /* camera.h:20-22 */
+
+/* ------------------------------------------------------------------------- */
+/* Error codes                                                               */
+/* ------------------------------------------------------------------------- */
+enum {
+	RT_OK              = 0,
+	RT_ERR_NO_DEVICE   = -1,   /* no CUDA device / driver: there is no CPU fallback */
+	RT_ERR_CUDA        = -2,   /* a CUDA runtime call failed */
+	RT_ERR_ARG         = -3,   /* invalid argument */
+	RT_ERR_STATE       = -4,   /* missing init / scene / skybox */
+	RT_ERR_NOMEM       = -5,
+	RT_ERR_PARSE       = -6,
+	RT_ERR_IO          = -7,
+};
+
+const char *rt_cuda_last_error(void);
+
+/* ------------------------------------------------------------------------- */
+/* Host side kept from the reference                                          */
+/* ------------------------------------------------------------------------- */
+
+/* scene.c:611-624 -- same grammar, same float construction, same messages on
+ * stderr, same return convention.  Writes the same bytes the reference writes
+ * (fields of each Object it assigns; union tail / padding are left untouched). */
+bool rt_parse_scene_file(const char *file, RtScene *scene);
+bool rt_parse_scene_string(const char *src, size_t len, RtScene *scene);
+
+/* Large-scene variant: same grammar, heap array, no 1024 cap.
+ * *objects is malloc'ed; release with rt_free_objects(). */
+int  rt_parse_scene_file_large(const char *file, RtObject **objects, int *num_objects);
+int  rt_parse_scene_string_large(const char *src, size_t len, RtObject **objects, int *num_objects);
+void rt_free_objects(RtObject *objects);
+
+/* camera.c:37-93 -- process-global pose with the reference's mutators. */
+void      rt_camera_reset(void);
+void      rt_move_camera(RtDirection dir, float speed);          /* camera.c:80-88  */
+void      rt_rotate_camera(double mouse_x, double mouse_y);      /* camera.c:42-78  */
+RtVector3 rt_get_camera_pos(void);                               /* camera.c:37-40  */
+RtCamera  rt_camera_snapshot(void);
+
+/* main.c:666-670 quantisation rule: (uint8_t)(x*255), row order unchanged. */
+void rt_quantize_frame(const float *frame_rgb, size_t num_pixels, uint8_t *out_rgb);
+
+/* ------------------------------------------------------------------------- */
+/* Device lifecycle                                                          */
+/* ------------------------------------------------------------------------- */
+
+/* Single-process mode: use GPUs [0, num_gpus) (num_gpus <= 0 -> 1).  Rows are
+ * split into contiguous bands, one per GPU, composited into GPU 0 over
+ * NVLink P2P. */
+int  rt_cuda_init(int num_gpus);
+/* One-process-per-GPU mode (torchrun ranks): bind to exactly this device. */
+int  rt_cuda_init_device(int device);
+void rt_cuda_shutdown(void);
+int  rt_cuda_num_gpus(void);
+
+/* AoS -> device SoA.  Scenes above RT_LBVH_THRESHOLD objects also get a device
+ * LBVH whose hits tie-break by primitive index (== the reference's linear scan). */
+int  rt_cuda_upload_scene(const RtScene *scene);
+int  rt_cuda_upload_objects(const RtObject *objects, int num_objects);
+int  rt_cuda_upload_skybox(const RtCubemap *sky);
+
+#define RT_LBVH_THRESHOLD 64
+
+/* ------------------------------------------------------------------------- */
+/* Rendering                                                                 */
+/* ------------------------------------------------------------------------- */
+
+enum { RT_FB_F32X3 = 0,    /* reference `Vector3*` frame: 12 B/px, bottom row first */
+       RT_FB_U8X4  = 1 };  /* (uint8_t)(x*255) per channel + alpha 255, 4 B/px      */
+
+enum { RT_VARIANT_EXACT = 0,  /* no FMA contraction, IEEE div/sqrt, f64 where C promotes: bit-exact */
+       RT_VARIANT_FAST  = 1 };/* FMA contraction allowed: <= 1 LSB (8-bit) on >= 99.9 % of pixels */
+
+enum { RT_TRAVERSAL_AUTO = 0, RT_TRAVERSAL_LINEAR = 1, RT_TRAVERSAL_LBVH = 2 };
+
+enum { RT_MEM_AUTO = 0, RT_MEM_HOST = 1, RT_MEM_DEVICE = 2 };
+
+enum { RT_KERNEL_AUTO = 0,
+       RT_KERNEL_PIXEL = 1,       /* one thread per low-res pixel, runs its whole path */
+       RT_KERNEL_PERSISTENT = 2 };/* persistent warps, lanes refill with new pixels as paths end */
+
+typedef struct {
+	uint32_t struct_size;   /* = sizeof(RtRenderOpts) */
+	int      scale;         /* render_column's scale: 1,2,4,8,16 (any >= 1) */
+	int      num_columns;   /* reference --threads; reproduces its column artefacts. default 1 */
+	uint64_t pass_index;    /* RNG key: state = key(u, v, pass_index) at the top of each pixel */
+	int      fb_format;     /* RT_FB_* */
+	int      fb_memory;     /* RT_MEM_*: where `fb` lives (AUTO = cudaPointerGetAttributes) */
+	int      row_begin;     /* band [row_begin,row_end) of output rows; 0,0 = whole frame. */
+	int      row_end;       /*   must be multiples of scale (except row_end == h) */
+	int      accumulate;    /* 0: fb <- this pass.  1: accum += pass/scale^2; fb <- accum/count */
+	int      variant;       /* RT_VARIANT_* */
+	int      traversal;     /* RT_TRAVERSAL_* */
+	int      kernel;        /* RT_KERNEL_* */
+	int      band_only_fb;  /* 1: fb holds only the band's rows (row_begin maps to fb row 0) */
+	void    *stream;        /* cudaStream_t to launch on in one-device mode; NULL = library stream */
+} RtRenderOpts;
+
+typedef struct {
+	uint64_t rays;          /* trace_ray-equivalent invocations of this call */
+	uint64_t pixels;        /* low-res pixels evaluated */
+	float    render_ms;     /* device time of the render kernels (max over GPUs) */
+	float    composite_ms;  /* device time of the band composite to GPU 0 (0 for 1 GPU) */
+	float    copy_ms;       /* device->host copy if fb is host memory */
+	int      kernel_launches;
+} RtRenderStats;
+
+void rt_render_opts_default(RtRenderOpts *opts);
+
+/* north_star signature.  `scene` may be NULL to reuse the uploaded scene; when
+ * non-NULL it is (re)uploaded if its contents changed.  fb: w*h RtVector3
+ * (host or device memory), bottom row first, values clamped to [0,1]. */
+int render_frame_cuda(const RtScene *scene, const RtCamera *cam, void *fb, int w, int h, int scale);
+
+int render_frame_cuda_ex(const RtCamera *cam, void *fb, int w, int h,
+                         const RtRenderOpts *opts, RtRenderStats *stats);
+
+/* invalidate_accumulation() (main.c:115-124): zero accum and the weight. */
+int   rt_cuda_accum_reset(void);
+float rt_cuda_accum_count(void);
+
+/* Progressive refinement as the reference's workers do after an invalidation
+ * (main.c:354,402-403): passes at init_scale, init_scale/2, ..., 1 with
+ * pass_index first_pass, first_pass+1, ..., each accumulated and resolved;
+ * fb holds the resolved frame after the last pass.  opts->scale/accumulate
+ * are ignored. */
+int rt_cuda_render_sweep(const RtCamera *cam, void *fb, int w, int h, int init_scale,
+                         uint64_t first_pass, const RtRenderOpts *opts, RtRenderStats *stats);
+
+/* Block until all work issued by the library has finished. */
+int rt_cuda_synchronize(void);
+
+/* ------------------------------------------------------------------------- */
+/* Unit-level device probes (used by the parity tests; thin wrappers over the */
+/* same device functions the render kernels inline)                          */
+/* ------------------------------------------------------------------------- */
+/* rays6: n x (origin xyz, direction xyz); out7: n x (distance, point, normal) */
+int rt_cuda_debug_trace(const float *rays6, int n, float *out7, int32_t *obj, int variant, int traversal);
+int rt_cuda_debug_sample_cubemap(const float *dirs3, int n, float *out3);
+int rt_cuda_debug_camera_rays(const RtCamera *cam, const float *pxpy, int n, float aspect, float *rays6);
+int rt_cuda_debug_rng(uint64_t state, int n, uint64_t *u64_out, float *f32_out);
+int rt_cuda_debug_random_directions(uint64_t state, int n, float *out3);
+uint64_t rt_pixel_key(float px, float py, uint64_t pass_index);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_CUDA_H */

@@ -1,0 +1,819 @@
+/*
+ * rt_api.cu -- the C ABI of include/rt_cuda.h: device lifecycle, scene/skybox
+ * upload (AoS -> SoA in HBM, LBVH for large scenes), the render entry points
+ * that replace the reference's worker pool (src/main.c:324-414, 450-482) with
+ * kernel launches, row-band multi-GPU rendering with a fused P2P composite, and
+ * the unit probes used by the parity tests.
+ *
+ * There is deliberately no CPU path in this file: every rendering entry point
+ * fails with RT_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#include <cuda_runtime.h>
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "rt_cuda.h"
+#include "rt_host.h"
+#include "rt_params.h"
+#include "rt_lbvh.h"
+
+/* launchers exported by the two builds of rt_render.cu */
+#define DECLARE_VARIANT(ns)                                                                              \
+	extern "C" cudaError_t ns##_launch_render(const RtRenderParams *, int, int, int, cudaStream_t);      \
+	extern "C" cudaError_t ns##_persistent_blocks_per_sm(const RtRenderParams *, int, int *);            \
+	extern "C" cudaError_t ns##_launch_probe_trace(const RtRenderParams *, int, const float *, int,      \
+	                                               float *, int *, cudaStream_t);                        \
+	extern "C" cudaError_t ns##_launch_probe_sky(const RtSkyView *, const float *, const float *, int,   \
+	                                             float *, cudaStream_t);                                 \
+	extern "C" cudaError_t ns##_launch_probe_camera(const RtCameraFrame *, const float *, int, float *,  \
+	                                                cudaStream_t);                                       \
+	extern "C" cudaError_t ns##_launch_probe_rng(uint64_t, int, uint64_t *, float *, float *, cudaStream_t);
+DECLARE_VARIANT(rt_exact)
+DECLARE_VARIANT(rt_fast)
+
+/* ------------------------------------------------------------------ errors */
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+	return code;
+}
+
+extern "C" const char *rt_cuda_last_error(void) { return g_err; }
+
+#define CU(call)                                                                                     \
+	do {                                                                                             \
+		cudaError_t e_ = (call);                                                                     \
+		if (e_ != cudaSuccess)                                                                       \
+			return fail(RT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),        \
+			            __FILE__, __LINE__);                                                         \
+	} while (0)
+
+/* ----------------------------------------------------------------- context */
+
+#define RT_MAX_GPUS 16
+
+struct DeviceCtx {
+	int          device = -1;
+	int          sm_count = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t  ev[4] = {nullptr, nullptr, nullptr, nullptr};
+	/* scene */
+	float4 *geomA = nullptr, *geomB = nullptr, *mat = nullptr;
+	RtLbvh  bvh;
+	/* skybox */
+	uchar4 *sky = nullptr;
+	float  *lut = nullptr;
+	/* outputs */
+	void   *fb = nullptr;       size_t fb_bytes = 0;      /* internal framebuffer (host destinations) */
+	float  *accum = nullptr;    size_t accum_bytes = 0;
+	int     accum_w = 0, accum_h = 0, accum_row0 = 0, accum_rows = 0;
+	unsigned long long *ray_counter = nullptr;
+	unsigned int       *work_counter = nullptr;
+	unsigned long long *host_rays = nullptr;              /* pinned */
+};
+
+struct Context {
+	bool      ready = false;
+	int       ngpu = 0;
+	DeviceCtx dev[RT_MAX_GPUS];
+	/* scene meta (identical on every device) */
+	int       n = 0, light_index = -1;
+	RtVector3 light_pos = {0, 0, 0};
+	bool      have_scene = false, have_bvh = false;
+	int       sky_w = 0, sky_h = 0;
+	bool      have_sky = false;
+	RtScene  *scene_cache = nullptr;    /* copy of the last RtScene given to render_frame_cuda */
+	float     accum_count = 0.0f;       /* accum_counts[] of main.c:89 (all columns advance together) */
+};
+
+static Context g;
+
+static int select_device(const DeviceCtx &d)
+{
+	CU(cudaSetDevice(d.device));
+	return RT_OK;
+}
+
+static void free_device(DeviceCtx &d)
+{
+	if (d.device < 0) return;
+	cudaSetDevice(d.device);
+	cudaFree(d.geomA); cudaFree(d.geomB); cudaFree(d.mat);
+	rt_lbvh_free(&d.bvh);
+	cudaFree(d.sky); cudaFree(d.lut);
+	cudaFree(d.fb); cudaFree(d.accum);
+	cudaFree(d.ray_counter); cudaFree(d.work_counter);
+	if (d.host_rays) cudaFreeHost(d.host_rays);
+	for (auto &e : d.ev) if (e) cudaEventDestroy(e);
+	if (d.stream) cudaStreamDestroy(d.stream);
+	d = DeviceCtx();
+}
+
+static int init_devices(const int *devices, int count)
+{
+	int available = 0;
+	cudaError_t e = cudaGetDeviceCount(&available);
+	if (e != cudaSuccess || available <= 0)
+		return fail(RT_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+		            e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+	if (count > RT_MAX_GPUS) return fail(RT_ERR_ARG, "at most %d GPUs", RT_MAX_GPUS);
+	for (int i = 0; i < count; i++)
+		if (devices[i] < 0 || devices[i] >= available)
+			return fail(RT_ERR_ARG, "device %d not present (%d visible)", devices[i], available);
+
+	rt_cuda_shutdown();
+	g.ngpu = count;
+	for (int i = 0; i < count; i++) {
+		DeviceCtx &d = g.dev[i];
+		d.device = devices[i];
+		CU(cudaSetDevice(d.device));
+		CU(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, d.device));
+		CU(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+		for (auto &ev : d.ev) CU(cudaEventCreate(&ev));
+		CU(cudaMalloc(&d.ray_counter, sizeof(unsigned long long)));
+		CU(cudaMalloc(&d.work_counter, sizeof(unsigned int)));
+		CU(cudaMemset(d.ray_counter, 0, sizeof(unsigned long long)));
+		CU(cudaMallocHost(&d.host_rays, sizeof(unsigned long long)));
+		float lut[256];
+		rt_host_byte_lut(lut);
+		CU(cudaMalloc(&d.lut, sizeof(lut)));
+		CU(cudaMemcpy(d.lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
+	}
+	/* band GPUs store straight into GPU 0's framebuffer over NVLink */
+	for (int i = 1; i < count; i++) {
+		int can = 0;
+		CU(cudaDeviceCanAccessPeer(&can, g.dev[i].device, g.dev[0].device));
+		if (!can) return fail(RT_ERR_CUDA, "GPU %d cannot access GPU %d peer memory", g.dev[i].device, g.dev[0].device);
+		CU(cudaSetDevice(g.dev[i].device));
+		cudaError_t pe = cudaDeviceEnablePeerAccess(g.dev[0].device, 0);
+		if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled)
+			return fail(RT_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(pe));
+		cudaGetLastError();
+	}
+	CU(cudaSetDevice(g.dev[0].device));
+	g.ready = true;
+	return RT_OK;
+}
+
+extern "C" int rt_cuda_init(int num_gpus)
+{
+	if (num_gpus <= 0) num_gpus = 1;
+	int devs[RT_MAX_GPUS];
+	for (int i = 0; i < num_gpus && i < RT_MAX_GPUS; i++) devs[i] = i;
+	return init_devices(devs, num_gpus);
+}
+
+extern "C" int rt_cuda_init_device(int device) { return init_devices(&device, 1); }
+
+extern "C" void rt_cuda_shutdown(void)
+{
+	for (int i = 0; i < g.ngpu; i++) free_device(g.dev[i]);
+	free(g.scene_cache);
+	g = Context();
+}
+
+extern "C" int rt_cuda_num_gpus(void) { return g.ready ? g.ngpu : 0; }
+
+static int require_ready(void)
+{
+	if (!g.ready) {
+		int rc = rt_cuda_init(1);       /* lazy single-GPU init, like the north_star one-call API */
+		if (rc != RT_OK) return rc;
+	}
+	return RT_OK;
+}
+
+extern "C" int rt_cuda_synchronize(void)
+{
+	if (!g.ready) return RT_OK;
+	for (int i = 0; i < g.ngpu; i++) {
+		CU(cudaSetDevice(g.dev[i].device));
+		CU(cudaStreamSynchronize(g.dev[i].stream));
+	}
+	CU(cudaSetDevice(g.dev[0].device));
+	return RT_OK;
+}
+
+/* ------------------------------------------------------------------ upload */
+
+extern "C" int rt_cuda_upload_objects(const RtObject *objects, int n)
+{
+	int rc = require_ready();
+	if (rc != RT_OK) return rc;
+	if (n < 0 || (n > 0 && !objects)) return fail(RT_ERR_ARG, "bad object array");
+	RtPackedScene ps;
+	rc = rt_host_pack_scene(objects, n, &ps);
+	if (rc != RT_OK) return fail(rc, "out of host memory packing %d objects", n);
+
+	size_t cnt = n > 0 ? (size_t) n : 1;
+	bool want_bvh = n > RT_LBVH_THRESHOLD;
+	for (int i = 0; i < g.ngpu; i++) {
+		DeviceCtx &d = g.dev[i];
+		if ((rc = select_device(d)) != RT_OK) { rt_host_free_packed(&ps); return rc; }
+		cudaStreamSynchronize(d.stream);
+		cudaFree(d.geomA); cudaFree(d.geomB); cudaFree(d.mat);
+		d.geomA = d.geomB = d.mat = nullptr;
+		rt_lbvh_free(&d.bvh);
+		cudaError_t e;
+		if ((e = cudaMalloc(&d.geomA, cnt * sizeof(float4))) != cudaSuccess ||
+		    (e = cudaMalloc(&d.geomB, cnt * sizeof(float4))) != cudaSuccess ||
+		    (e = cudaMalloc(&d.mat, cnt * RT_MAT_STRIDE * sizeof(float4))) != cudaSuccess ||
+		    (e = cudaMemcpy(d.geomA, ps.geomA, cnt * sizeof(float4), cudaMemcpyHostToDevice)) != cudaSuccess ||
+		    (e = cudaMemcpy(d.geomB, ps.geomB, cnt * sizeof(float4), cudaMemcpyHostToDevice)) != cudaSuccess ||
+		    (e = cudaMemcpy(d.mat, ps.mat, cnt * RT_MAT_STRIDE * sizeof(float4), cudaMemcpyHostToDevice)) != cudaSuccess) {
+			rt_host_free_packed(&ps);
+			return fail(RT_ERR_CUDA, "scene upload: %s", cudaGetErrorString(e));
+		}
+		if (want_bvh) {
+			rc = rt_lbvh_build(&d.bvh, d.geomA, d.geomB, n, &ps, d.stream);
+			if (rc != RT_OK) {
+				rt_host_free_packed(&ps);
+				return fail(rc, "LBVH build failed: %s", rt_lbvh_last_error());
+			}
+		}
+	}
+	g.n = n;
+	g.light_index = ps.light_index;
+	g.light_pos = ps.light_pos;
+	g.have_scene = true;
+	g.have_bvh = want_bvh;
+	rt_host_free_packed(&ps);
+	cudaSetDevice(g.dev[0].device);
+	return RT_OK;
+}
+
+extern "C" int rt_cuda_upload_scene(const RtScene *scene)
+{
+	if (!scene) return fail(RT_ERR_ARG, "scene is NULL");
+	if (scene->num_objects < 0 || scene->num_objects > RT_MAX_OBJECTS)
+		return fail(RT_ERR_ARG, "scene->num_objects = %d out of range", scene->num_objects);
+	int rc = rt_cuda_upload_objects(scene->objects, scene->num_objects);
+	if (rc != RT_OK) return rc;
+	if (!g.scene_cache) g.scene_cache = (RtScene *) malloc(sizeof(RtScene));
+	if (g.scene_cache) {
+		memcpy(g.scene_cache->objects, scene->objects, sizeof(RtObject) * (size_t) scene->num_objects);
+		g.scene_cache->num_objects = scene->num_objects;
+	}
+	return RT_OK;
+}
+
+extern "C" int rt_cuda_upload_skybox(const RtCubemap *sky)
+{
+	int rc = require_ready();
+	if (rc != RT_OK) return rc;
+	if (!sky || sky->w <= 0 || sky->h <= 0 || sky->chan < 3)
+		return fail(RT_ERR_ARG, "skybox must have w,h > 0 and >= 3 channels (sample_cubemap reads RGB)");
+	for (int f = 0; f < 6; f++)
+		if (!sky->data[f]) return fail(RT_ERR_ARG, "skybox face %d is NULL", f);
+
+	/* RGB(A) rows -> RGBA8 so a texel is one aligned 4-byte load */
+	size_t face = (size_t) sky->w * sky->h;
+	std::vector<uchar4> staged;
+	try { staged.resize(6 * face); } catch (...) { return fail(RT_ERR_NOMEM, "out of host memory staging the skybox"); }
+	for (int f = 0; f < 6; f++) {
+		const uint8_t *src = sky->data[f];
+		uchar4 *dst = staged.data() + (size_t) f * face;
+		for (size_t p = 0; p < face; p++) {
+			const uint8_t *t = src + p * (size_t) sky->chan;
+			dst[p] = make_uchar4(t[0], t[1], t[2], 255);
+		}
+	}
+	for (int i = 0; i < g.ngpu; i++) {
+		DeviceCtx &d = g.dev[i];
+		if ((rc = select_device(d)) != RT_OK) return rc;
+		cudaStreamSynchronize(d.stream);
+		cudaFree(d.sky);
+		d.sky = nullptr;
+		CU(cudaMalloc(&d.sky, 6 * face * sizeof(uchar4)));
+		CU(cudaMemcpy(d.sky, staged.data(), 6 * face * sizeof(uchar4), cudaMemcpyHostToDevice));
+	}
+	g.sky_w = sky->w;
+	g.sky_h = sky->h;
+	g.have_sky = true;
+	cudaSetDevice(g.dev[0].device);
+	return RT_OK;
+}
+
+/* ------------------------------------------------------------------ render */
+
+extern "C" void rt_render_opts_default(RtRenderOpts *o)
+{
+	memset(o, 0, sizeof(*o));
+	o->struct_size = sizeof(*o);
+	o->scale = 1;
+	o->num_columns = 1;
+	o->fb_format = RT_FB_F32X3;
+	o->fb_memory = RT_MEM_AUTO;
+	o->variant = RT_VARIANT_EXACT;
+	o->traversal = RT_TRAVERSAL_AUTO;
+	o->kernel = RT_KERNEL_AUTO;
+}
+
+static size_t bytes_per_pixel(int fmt) { return fmt == RT_FB_U8X4 ? 4 : 12; }
+
+static bool is_device_pointer(const void *p)
+{
+	cudaPointerAttributes a;
+	cudaError_t e = cudaPointerGetAttributes(&a, p);
+	if (e != cudaSuccess) { cudaGetLastError(); return false; }
+	return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+static void fill_views(const DeviceCtx &d, RtRenderParams &P)
+{
+	P.scene.geomA = d.geomA;
+	P.scene.geomB = d.geomB;
+	P.scene.mat = d.mat;
+	P.scene.n = g.n;
+	P.scene.light_index = g.light_index;
+	P.scene.light_pos = g.light_pos;
+	P.bvh = rt_lbvh_view(&d.bvh);
+	P.sky.texels = d.sky;
+	P.sky.w = g.sky_w;
+	P.sky.h = g.sky_h;
+	P.sky.face_stride = (size_t) g.sky_w * g.sky_h;
+	P.byte_lut = d.lut;
+	P.ray_counter = d.ray_counter;
+	P.work_counter = d.work_counter;
+}
+
+static int pick_traversal(int requested, bool *lbvh)
+{
+	if (requested == RT_TRAVERSAL_LBVH) {
+		if (!g.have_bvh) return fail(RT_ERR_STATE, "LBVH traversal requested but the scene has <= %d objects (no LBVH built)", RT_LBVH_THRESHOLD);
+		*lbvh = true;
+	} else if (requested == RT_TRAVERSAL_LINEAR) {
+		if (g.n > RT_SMEM_MAX_OBJECTS)
+			return fail(RT_ERR_ARG, "linear scan is limited to %d objects (shared-memory staging)", RT_SMEM_MAX_OBJECTS);
+		*lbvh = false;
+	} else
+		*lbvh = g.have_bvh;
+	return RT_OK;
+}
+
+static int ensure_accum(DeviceCtx &d, int w, int h, int row0, int rows, bool *fresh)
+{
+	size_t need = (size_t) w * rows * 3 * sizeof(float);
+	if (d.accum && d.accum_w == w && d.accum_h == h && d.accum_row0 == row0 && d.accum_rows == rows) return RT_OK;
+	*fresh = true;
+	CU(cudaFree(d.accum));
+	d.accum = nullptr;
+	CU(cudaMalloc(&d.accum, need ? need : 4));
+	CU(cudaMemsetAsync(d.accum, 0, need, d.stream));
+	d.accum_bytes = need;
+	d.accum_w = w; d.accum_h = h; d.accum_row0 = row0; d.accum_rows = rows;
+	return RT_OK;
+}
+
+extern "C" int rt_cuda_accum_reset(void)
+{
+	g.accum_count = 0.0f;
+	if (!g.ready) return RT_OK;
+	for (int i = 0; i < g.ngpu; i++) {
+		DeviceCtx &d = g.dev[i];
+		if (!d.accum) continue;
+		int rc = select_device(d);
+		if (rc != RT_OK) return rc;
+		CU(cudaMemsetAsync(d.accum, 0, d.accum_bytes, d.stream));
+	}
+	cudaSetDevice(g.dev[0].device);
+	return RT_OK;
+}
+
+extern "C" float rt_cuda_accum_count(void) { return g.accum_count; }
+
+/* fb[p] = accum[p] * inv_count (main.c:467-477) over whole rows; used when a pass
+ * leaves pixels uncovered (rows >= (h/scale)*scale, columns >= T*(w/T)): their
+ * data counts as 0, but the frame is still accum / count everywhere. */
+__global__ void resolve_rows_kernel(const float *accum, size_t accum_first, void *fb, size_t fb_first,
+                                    int fmt, size_t count, float inv)
+{
+	size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+	if (i >= count) return;
+	const float *a = accum + 3 * (accum_first + i);
+	float r = a[0] * inv, gch = a[1] * inv, b = a[2] * inv;
+	size_t p = fb_first + i;
+	if (fmt == RT_FB_F32X3) {
+		float *f = reinterpret_cast<float *>(fb) + 3 * p;
+		f[0] = r; f[1] = gch; f[2] = b;
+	} else {
+		reinterpret_cast<uchar4 *>(fb)[p] = make_uchar4((unsigned char) __float2uint_rz(r * 255.0f),
+		                                                (unsigned char) __float2uint_rz(gch * 255.0f),
+		                                                (unsigned char) __float2uint_rz(b * 255.0f), 255);
+	}
+}
+
+struct PassPlan {
+	int  w, h, scale, ncols;
+	int  row0, row1;          /* output band of the whole call */
+	bool lbvh, persistent, exact;
+};
+
+/* Launch one pass for one device over output rows [r0, r1) (scale aligned). */
+static int launch_band(DeviceCtx &d, const RtCamera *cam, const PassPlan &pl, const RtRenderOpts *o,
+                       void *fb, int fb_row_offset, int r0, int r1, cudaStream_t stream, bool accumulate,
+                       float accum_weight, float inv_count, int *launches)
+{
+	RtRenderParams P;
+	memset(&P, 0, sizeof(P));
+	fill_views(d, P);
+	rt_host_camera_frame(cam, (float) pl.w / pl.h, &P.cam);       /* main.c:281 aspect */
+	P.W = pl.w; P.H = pl.h; P.scale = pl.scale;
+	P.num_columns = pl.ncols;
+	P.column_w = pl.w / pl.ncols;                                   /* main.c:363 */
+	P.lw = pl.w / pl.scale;                                         /* main.c:284-285 */
+	P.lh = pl.h / pl.scale;
+	P.cells_per_col = (P.column_w + pl.scale - 1) / pl.scale;
+	P.cells_per_row = pl.ncols * P.cells_per_col;
+	P.lrow0 = r0 / pl.scale;
+	P.lrow1 = std::min((r1 + pl.scale - 1) / pl.scale, P.lh);
+	if (P.lrow1 < P.lrow0) P.lrow1 = P.lrow0;
+	P.tiles_x = (P.cells_per_row + RT_TILE_W - 1) / RT_TILE_W;
+	P.tiles_y = (P.lrow1 - P.lrow0 + RT_TILE_H - 1) / RT_TILE_H;
+	P.pass_mix = rt_host_splitmix64(o->pass_index);
+	P.fb = fb;
+	P.fb_format = o->fb_format;
+	P.fb_row_offset = fb_row_offset;
+	P.accum = accumulate ? d.accum : nullptr;
+	P.accum_row_offset = d.accum_row0;
+	P.accum_weight = accum_weight;
+	P.inv_count = inv_count;
+
+	/* Pixels the reference's pass never writes (main.c:285-290: rows >=
+	 * lh*scale; main.c:363: columns >= T*column_w): a fresh frame holds 0 there,
+	 * an accumulated frame keeps accum/count. */
+	int covered_rows_end = std::min(P.lh * pl.scale, r1);
+	bool uncovered = covered_rows_end < r1 || P.column_w * pl.ncols < pl.w;
+	size_t bpp = bytes_per_pixel(o->fb_format);
+	if (uncovered && !accumulate) {
+		int s0 = P.column_w * pl.ncols < pl.w ? r0 : std::max(covered_rows_end, r0);
+		CU(cudaMemsetAsync((char *) fb + (size_t) (s0 - fb_row_offset) * pl.w * bpp, 0,
+		                   (size_t) (r1 - s0) * pl.w * bpp, stream));
+		(*launches)++;
+	}
+
+	if (P.tiles_x > 0 && P.tiles_y > 0) {
+		int grid = 0;
+		if (pl.persistent) {
+			CU(cudaMemsetAsync(d.work_counter, 0, sizeof(unsigned int), stream));
+			int per_sm = 0;
+			CU((pl.exact ? rt_exact_persistent_blocks_per_sm : rt_fast_persistent_blocks_per_sm)(&P, pl.lbvh, &per_sm));
+			if (per_sm < 1) per_sm = 1;
+			unsigned warps_needed = (unsigned) P.tiles_x * P.tiles_y;
+			unsigned blocks_needed = (warps_needed + (RT_BLOCK_THREADS / 32) - 1) / (RT_BLOCK_THREADS / 32);
+			grid = (int) std::min<unsigned>((unsigned) (d.sm_count * per_sm), blocks_needed);
+		}
+		CU((pl.exact ? rt_exact_launch_render : rt_fast_launch_render)(&P, pl.lbvh, pl.persistent, grid, stream));
+		(*launches)++;
+	}
+
+	if (uncovered && accumulate) {
+		size_t count = (size_t) (r1 - r0) * pl.w;
+		resolve_rows_kernel<<<(unsigned) ((count + 255) / 256), 256, 0, stream>>>(
+		    d.accum, (size_t) (r0 - d.accum_row0) * pl.w, fb, (size_t) (r0 - fb_row_offset) * pl.w,
+		    o->fb_format, count, inv_count);
+		CU(cudaGetLastError());
+		(*launches)++;
+	}
+	return RT_OK;
+}
+
+static int validate_common(const RtCamera *cam, void *fb, int w, int h, const RtRenderOpts *o)
+{
+	if (!cam || !fb) return fail(RT_ERR_ARG, "camera and framebuffer must be non-NULL");
+	if (w <= 0 || h <= 0) return fail(RT_ERR_ARG, "bad frame size %dx%d", w, h);
+	if (!o || o->struct_size != sizeof(RtRenderOpts)) return fail(RT_ERR_ARG, "opts->struct_size mismatch (ABI)");
+	if (o->scale < 1) return fail(RT_ERR_ARG, "scale must be >= 1");
+	if (o->num_columns < 1 || o->num_columns > w) return fail(RT_ERR_ARG, "num_columns out of range");
+	if (o->fb_format != RT_FB_F32X3 && o->fb_format != RT_FB_U8X4) return fail(RT_ERR_ARG, "unknown fb_format");
+	if (o->variant != RT_VARIANT_EXACT && o->variant != RT_VARIANT_FAST) return fail(RT_ERR_ARG, "unknown variant");
+	if (!g.have_scene) return fail(RT_ERR_STATE, "no scene uploaded (rt_cuda_upload_scene)");
+	if (!g.have_sky) return fail(RT_ERR_STATE, "no skybox uploaded (rt_cuda_upload_skybox)");
+	return RT_OK;
+}
+
+static int render_pass(const RtCamera *cam, void *fb, int w, int h, const RtRenderOpts *o,
+                       bool accumulate, RtRenderStats *stats, bool sync_and_copy)
+{
+	PassPlan pl;
+	pl.w = w; pl.h = h; pl.scale = o->scale; pl.ncols = o->num_columns;
+	pl.row0 = o->row_begin; pl.row1 = o->row_end;
+	if (pl.row0 == 0 && pl.row1 == 0) pl.row1 = h;
+	if (pl.row0 < 0 || pl.row1 > h || pl.row0 >= pl.row1) return fail(RT_ERR_ARG, "bad row band [%d,%d)", pl.row0, pl.row1);
+	if (pl.row0 % pl.scale != 0 || (pl.row1 % pl.scale != 0 && pl.row1 != h))
+		return fail(RT_ERR_ARG, "row band must be aligned to scale");
+	int rc = pick_traversal(o->traversal, &pl.lbvh);
+	if (rc != RT_OK) return rc;
+	pl.exact = o->variant == RT_VARIANT_EXACT;
+	pl.persistent = o->kernel == RT_KERNEL_PERSISTENT || (o->kernel == RT_KERNEL_AUTO);
+
+	size_t bpp = bytes_per_pixel(o->fb_format);
+	int band_rows = pl.row1 - pl.row0;
+	int fb_row_offset = o->band_only_fb ? pl.row0 : 0;
+	size_t fb_rows = o->band_only_fb ? (size_t) band_rows : (size_t) h;
+
+	bool dev_fb = o->fb_memory == RT_MEM_DEVICE || (o->fb_memory == RT_MEM_AUTO && is_device_pointer(fb));
+	DeviceCtx &d0 = g.dev[0];
+	void *target = fb;
+	if (!dev_fb) {
+		size_t need = fb_rows * (size_t) w * bpp;
+		if ((rc = select_device(d0)) != RT_OK) return rc;
+		if (d0.fb_bytes < need) {
+			CU(cudaFree(d0.fb));
+			d0.fb = nullptr; d0.fb_bytes = 0;
+			CU(cudaMalloc(&d0.fb, need));
+			d0.fb_bytes = need;
+		}
+		target = d0.fb;
+	}
+
+	int ngpu = g.ngpu;
+	bool use_user_stream = ngpu == 1 && o->stream != nullptr;
+	int launches = 0;
+
+	/* contiguous row bands, aligned to scale */
+	int band_r0[RT_MAX_GPUS], band_r1[RT_MAX_GPUS];
+	int lrows = (band_rows + pl.scale - 1) / pl.scale;
+	int start_l = 0;
+	bool fresh_accum = false;
+	for (int i = 0; i < ngpu; i++) {
+		int take = lrows / ngpu + (i < lrows % ngpu ? 1 : 0);
+		band_r0[i] = pl.row0 + start_l * pl.scale;
+		band_r1[i] = std::min(pl.row0 + (start_l + take) * pl.scale, pl.row1);
+		start_l += take;
+		DeviceCtx &d = g.dev[i];
+		if ((rc = select_device(d)) != RT_OK) return rc;
+		if (accumulate && band_r1[i] > band_r0[i] &&
+		    (rc = ensure_accum(d, w, h, band_r0[i], band_r1[i] - band_r0[i], &fresh_accum)) != RT_OK) return rc;
+		if (pl.lbvh) {
+			/* the LBVH padding covers ray origins up to d_max away (rt_lbvh.cu) */
+			float need = rt_lbvh_required_dmax(&d.bvh, cam->pos);
+			if (need > d.bvh.d_max) {
+				cudaStream_t st = use_user_stream ? (cudaStream_t) o->stream : d.stream;
+				if ((rc = rt_lbvh_refit(&d.bvh, d.geomA, d.geomB, need * 1.05f, st)) != RT_OK)
+					return fail(rc, "LBVH refit failed: %s", rt_lbvh_last_error());
+			}
+		}
+	}
+
+	/* accumulation weights (main.c:278, 394-396, 476) */
+	float wgt = 1.0f / (float) (pl.scale * pl.scale);
+	float inv = 1.0f;
+	if (accumulate) {
+		if (fresh_accum) g.accum_count = 0.0f;      /* buffers were (re)allocated: start over */
+		g.accum_count += wgt;
+		inv = 1.0f / g.accum_count;
+	}
+
+	for (int i = 0; i < ngpu; i++) {
+		DeviceCtx &d = g.dev[i];
+		int r0 = band_r0[i], r1 = band_r1[i];
+		if ((rc = select_device(d)) != RT_OK) return rc;
+		cudaStream_t st = use_user_stream ? (cudaStream_t) o->stream : d.stream;
+		if (stats) {
+			CU(cudaMemsetAsync(d.ray_counter, 0, sizeof(unsigned long long), st));
+			CU(cudaEventRecord(d.ev[0], st));
+		}
+		if (r1 > r0) {
+			rc = launch_band(d, cam, pl, o, target, fb_row_offset, r0, r1, st, accumulate, wgt, inv, &launches);
+			if (rc != RT_OK) return rc;
+		}
+		if (stats) CU(cudaEventRecord(d.ev[1], st));
+	}
+
+	if (!sync_and_copy && !stats && dev_fb) {
+		cudaSetDevice(d0.device);
+		return RT_OK;       /* fully asynchronous call */
+	}
+
+	/* wait for the bands; band GPUs wrote into GPU 0 memory directly (P2P) */
+	float render_ms = 0.0f;
+	unsigned long long rays = 0;
+	for (int i = 0; i < ngpu; i++) {
+		DeviceCtx &d = g.dev[i];
+		if ((rc = select_device(d)) != RT_OK) return rc;
+		cudaStream_t st = use_user_stream ? (cudaStream_t) o->stream : d.stream;
+		if (stats) {
+			CU(cudaMemcpyAsync(d.host_rays, d.ray_counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+		}
+		CU(cudaStreamSynchronize(st));
+		if (stats) {
+			float ms = 0.0f;
+			CU(cudaEventElapsedTime(&ms, d.ev[0], d.ev[1]));
+			render_ms = std::max(render_ms, ms);
+			rays += *d.host_rays;
+		}
+	}
+	if ((rc = select_device(d0)) != RT_OK) return rc;
+
+	float copy_ms = 0.0f;
+	if (!dev_fb) {
+		cudaStream_t st = use_user_stream ? (cudaStream_t) o->stream : d0.stream;
+		CU(cudaEventRecord(d0.ev[2], st));
+		CU(cudaMemcpyAsync(fb, d0.fb, fb_rows * (size_t) w * bpp, cudaMemcpyDeviceToHost, st));
+		CU(cudaEventRecord(d0.ev[3], st));
+		CU(cudaStreamSynchronize(st));
+		if (stats) CU(cudaEventElapsedTime(&copy_ms, d0.ev[2], d0.ev[3]));
+	}
+	if (stats) {
+		stats->rays = rays;
+		int lw = w / pl.scale;
+		(void) lw;
+		int colw = w / pl.ncols;
+		int cells_per_row = pl.ncols * ((colw + pl.scale - 1) / pl.scale);
+		int lh = h / pl.scale;
+		int l0 = pl.row0 / pl.scale, l1 = std::min((pl.row1 + pl.scale - 1) / pl.scale, lh);
+		stats->pixels = (uint64_t) cells_per_row * (uint64_t) std::max(l1 - l0, 0);
+		stats->render_ms = render_ms;
+		stats->composite_ms = 0.0f;    /* fused: band kernels store into GPU 0 over P2P */
+		stats->copy_ms = copy_ms;
+		stats->kernel_launches = launches;
+	}
+	return RT_OK;
+}
+
+extern "C" int render_frame_cuda_ex(const RtCamera *cam, void *fb, int w, int h, const RtRenderOpts *opts,
+                                    RtRenderStats *stats)
+{
+	int rc = require_ready();
+	if (rc != RT_OK) return rc;
+	RtRenderOpts def;
+	if (!opts) { rt_render_opts_default(&def); opts = &def; }
+	if ((rc = validate_common(cam, fb, w, h, opts)) != RT_OK) return rc;
+	return render_pass(cam, fb, w, h, opts, opts->accumulate != 0, stats, true);
+}
+
+extern "C" int render_frame_cuda(const RtScene *scene, const RtCamera *cam, void *fb, int w, int h, int scale)
+{
+	int rc = require_ready();
+	if (rc != RT_OK) return rc;
+	if (scene) {
+		bool same = g.have_scene && g.scene_cache && g.scene_cache->num_objects == scene->num_objects &&
+		            memcmp(g.scene_cache->objects, scene->objects, sizeof(RtObject) * (size_t) scene->num_objects) == 0;
+		if (!same && (rc = rt_cuda_upload_scene(scene)) != RT_OK) return rc;
+	}
+	RtRenderOpts o;
+	rt_render_opts_default(&o);
+	o.scale = scale;
+	if ((rc = validate_common(cam, fb, w, h, &o)) != RT_OK) return rc;
+	return render_pass(cam, fb, w, h, &o, false, nullptr, true);
+}
+
+extern "C" int rt_cuda_render_sweep(const RtCamera *cam, void *fb, int w, int h, int init_scale,
+                                    uint64_t first_pass, const RtRenderOpts *opts, RtRenderStats *stats)
+{
+	int rc = require_ready();
+	if (rc != RT_OK) return rc;
+	if (init_scale < 1 || (init_scale & (init_scale - 1))) return fail(RT_ERR_ARG, "init_scale must be a power of two");
+	RtRenderOpts o;
+	if (opts) o = *opts; else rt_render_opts_default(&o);
+	o.scale = init_scale;
+	if ((rc = validate_common(cam, fb, w, h, &o)) != RT_OK) return rc;
+	if ((rc = rt_cuda_accum_reset()) != RT_OK) return rc;          /* invalidate_accumulation() */
+	RtRenderStats total;
+	memset(&total, 0, sizeof(total));
+	uint64_t pass = first_pass;
+	bool dev_fb = o.fb_memory == RT_MEM_DEVICE || (o.fb_memory == RT_MEM_AUTO && is_device_pointer(fb));
+	for (int s = init_scale; s >= 1; s >>= 1, pass++) {             /* main.c:402-403 */
+		o.scale = s;
+		o.pass_index = pass;
+		RtRenderStats st;
+		memset(&st, 0, sizeof(st));
+		bool last = s == 1;
+		/* intermediate passes of a host-destination sweep stay on the device */
+		RtRenderOpts oo = o;
+		void *dst = fb;
+		if (!dev_fb && !last) {
+			size_t need = (size_t) w * h * bytes_per_pixel(o.fb_format);
+			DeviceCtx &d0 = g.dev[0];
+			if ((rc = select_device(d0)) != RT_OK) return rc;
+			if (d0.fb_bytes < need) {
+				CU(cudaFree(d0.fb));
+				d0.fb = nullptr; d0.fb_bytes = 0;
+				CU(cudaMalloc(&d0.fb, need));
+				d0.fb_bytes = need;
+			}
+			dst = d0.fb;
+			oo.fb_memory = RT_MEM_DEVICE;
+		}
+		rc = render_pass(cam, dst, w, h, &oo, true, stats ? &st : nullptr, last);
+		if (rc != RT_OK) return rc;
+		total.rays += st.rays; total.pixels += st.pixels;
+		total.render_ms += st.render_ms; total.copy_ms += st.copy_ms;
+		total.kernel_launches += st.kernel_launches;
+	}
+	if (stats) *stats = total;
+	return RT_OK;
+}
+
+/* ------------------------------------------------------------------ probes */
+
+struct TempBuf {
+	void *p = nullptr;
+	~TempBuf() { cudaFree(p); }
+	cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 4); }
+};
+
+extern "C" int rt_cuda_debug_trace(const float *rays6, int n, float *out7, int32_t *obj, int variant, int traversal)
+{
+	int rc = require_ready();
+	if (rc != RT_OK) return rc;
+	if (!g.have_scene) return fail(RT_ERR_STATE, "no scene uploaded");
+	bool lbvh;
+	if ((rc = pick_traversal(traversal, &lbvh)) != RT_OK) return rc;
+	DeviceCtx &d = g.dev[0];
+	if ((rc = select_device(d)) != RT_OK) return rc;
+	TempBuf r, o, ob;
+	CU(r.alloc(sizeof(float) * 6 * (size_t) n));
+	CU(o.alloc(sizeof(float) * 7 * (size_t) n));
+	CU(ob.alloc(sizeof(int) * (size_t) n));
+	CU(cudaMemcpyAsync(r.p, rays6, sizeof(float) * 6 * (size_t) n, cudaMemcpyHostToDevice, d.stream));
+	RtRenderParams P;
+	memset(&P, 0, sizeof(P));
+	fill_views(d, P);
+	CU((variant == RT_VARIANT_FAST ? rt_fast_launch_probe_trace : rt_exact_launch_probe_trace)(
+	    &P, lbvh, (const float *) r.p, n, (float *) o.p, (int *) ob.p, d.stream));
+	CU(cudaMemcpyAsync(out7, o.p, sizeof(float) * 7 * (size_t) n, cudaMemcpyDeviceToHost, d.stream));
+	CU(cudaMemcpyAsync(obj, ob.p, sizeof(int) * (size_t) n, cudaMemcpyDeviceToHost, d.stream));
+	CU(cudaStreamSynchronize(d.stream));
+	return RT_OK;
+}
+
+extern "C" int rt_cuda_debug_sample_cubemap(const float *dirs3, int n, float *out3)
+{
+	int rc = require_ready();
+	if (rc != RT_OK) return rc;
+	if (!g.have_sky) return fail(RT_ERR_STATE, "no skybox uploaded");
+	DeviceCtx &d = g.dev[0];
+	if ((rc = select_device(d)) != RT_OK) return rc;
+	TempBuf in, out;
+	CU(in.alloc(sizeof(float) * 3 * (size_t) n));
+	CU(out.alloc(sizeof(float) * 3 * (size_t) n));
+	CU(cudaMemcpyAsync(in.p, dirs3, sizeof(float) * 3 * (size_t) n, cudaMemcpyHostToDevice, d.stream));
+	RtRenderParams P;
+	memset(&P, 0, sizeof(P));
+	fill_views(d, P);
+	CU(rt_exact_launch_probe_sky(&P.sky, d.lut, (const float *) in.p, n, (float *) out.p, d.stream));
+	CU(cudaMemcpyAsync(out3, out.p, sizeof(float) * 3 * (size_t) n, cudaMemcpyDeviceToHost, d.stream));
+	CU(cudaStreamSynchronize(d.stream));
+	return RT_OK;
+}
+
+extern "C" int rt_cuda_debug_camera_rays(const RtCamera *cam, const float *pxpy, int n, float aspect, float *rays6)
+{
+	int rc = require_ready();
+	if (rc != RT_OK) return rc;
+	DeviceCtx &d = g.dev[0];
+	if ((rc = select_device(d)) != RT_OK) return rc;
+	TempBuf in, out;
+	CU(in.alloc(sizeof(float) * 2 * (size_t) n));
+	CU(out.alloc(sizeof(float) * 6 * (size_t) n));
+	CU(cudaMemcpyAsync(in.p, pxpy, sizeof(float) * 2 * (size_t) n, cudaMemcpyHostToDevice, d.stream));
+	RtCameraFrame cf;
+	rt_host_camera_frame(cam, aspect, &cf);
+	CU(rt_exact_launch_probe_camera(&cf, (const float *) in.p, n, (float *) out.p, d.stream));
+	CU(cudaMemcpyAsync(rays6, out.p, sizeof(float) * 6 * (size_t) n, cudaMemcpyDeviceToHost, d.stream));
+	CU(cudaStreamSynchronize(d.stream));
+	return RT_OK;
+}
+
+static int rng_probe(uint64_t state, int n, uint64_t *u64_out, float *f32_out, float *dir_out)
+{
+	int rc = require_ready();
+	if (rc != RT_OK) return rc;
+	DeviceCtx &d = g.dev[0];
+	if ((rc = select_device(d)) != RT_OK) return rc;
+	TempBuf u, f, v;
+	CU(u.alloc(sizeof(uint64_t) * (size_t) n));
+	CU(f.alloc(sizeof(float) * (size_t) n));
+	CU(v.alloc(sizeof(float) * 3 * (size_t) n));
+	CU(rt_exact_launch_probe_rng(state, n, u64_out ? (uint64_t *) u.p : nullptr, f32_out ? (float *) f.p : nullptr,
+	                             dir_out ? (float *) v.p : nullptr, d.stream));
+	if (u64_out) CU(cudaMemcpyAsync(u64_out, u.p, sizeof(uint64_t) * (size_t) n, cudaMemcpyDeviceToHost, d.stream));
+	if (f32_out) CU(cudaMemcpyAsync(f32_out, f.p, sizeof(float) * (size_t) n, cudaMemcpyDeviceToHost, d.stream));
+	if (dir_out) CU(cudaMemcpyAsync(dir_out, v.p, sizeof(float) * 3 * (size_t) n, cudaMemcpyDeviceToHost, d.stream));
+	CU(cudaStreamSynchronize(d.stream));
+	return RT_OK;
+}
+
+extern "C" int rt_cuda_debug_rng(uint64_t state, int n, uint64_t *u64_out, float *f32_out)
+{
+	return rng_probe(state, n, u64_out, f32_out, nullptr);
+}
+
+extern "C" int rt_cuda_debug_random_directions(uint64_t state, int n, float *out3)
+{
+	return rng_probe(state, n, nullptr, nullptr, out3);
+}

@@ -1,0 +1,311 @@
+/*
+ * rt_lbvh.cu -- device LBVH build (Morton codes -> radix sort -> Karras 2012
+ * hierarchy -> bottom-up refit) for scenes above RT_LBVH_THRESHOLD objects.
+ *
+ * Parity contract: traversal (rt_device.cuh: nearest_lbvh) must return what
+ * the reference's linear scan (scene.c:156-173) returns, bit for bit.  The
+ * per-primitive arithmetic is the same device function as the linear scan, and
+ * ties go to the lower primitive index; what the hierarchy must guarantee is
+ * that no primitive the reference would accept is ever culled.  The
+ * reference's sphere test is "fuzzy": c = oc.oc - r*r and discr = b*b - 4ac
+ * cancel in binary32 when the origin-centre distance D >> r, so it reports
+ * hits for rays that geometrically miss by m with m^2 <= r^2 + k*2^-24*D^2
+ * (measured k <= 5.6; a first-order error bound of the
+ * binary32 evaluation gives k ~ 15).  Boxes therefore bound the sphere of
+ * radius sqrt(r^2 + K*2^-24*D_max^2), K = 32, where D_max is the largest
+ * distance from any ray origin (camera or a surface point) to any primitive;
+ * cubes get a few-ulp pad, and a node is culled only when its entry distance
+ * exceeds best + t_slack (1e-3 * D_max), which also keeps equal-t candidates
+ * alive for the index tie-break.
+ */
+#include <cub/device/device_radix_sort.cuh>
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "rt_lbvh.h"
+#include "rt_cuda.h"
+
+static thread_local char lbvh_err[256] = "";
+const char *rt_lbvh_last_error(void) { return lbvh_err; }
+
+static int lfail(int code, const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(lbvh_err, sizeof(lbvh_err), fmt, ap);
+	va_end(ap);
+	return code;
+}
+
+#define LCU(call)                                                                                  \
+	do {                                                                                           \
+		cudaError_t e_ = (call);                                                                   \
+		if (e_ != cudaSuccess)                                                                     \
+			return lfail(RT_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_));                    \
+	} while (0)
+
+#define RT_FUZZ_K 32.0
+
+/* ---- Morton keys -------------------------------------------------------- */
+
+__device__ __forceinline__ unsigned int spread10(unsigned int v)
+{
+	v = (v * 0x00010001u) & 0xFF0000FFu;
+	v = (v * 0x00000101u) & 0x0F00F00Fu;
+	v = (v * 0x00000011u) & 0xC30C30C3u;
+	v = (v * 0x00000005u) & 0x49249249u;
+	return v;
+}
+
+__global__ void morton_kernel(const float4 *A, const float4 *B, int n, float3 lo, float3 inv_extent,
+                              unsigned long long *keys)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	float4 a = A[i], b = B[i];
+	float3 c;
+	if (__float_as_int(b.w) == RT_OBJECT_SPHERE) c = make_float3(a.x, a.y, a.z);
+	else c = make_float3(0.5f * (a.x + b.x), 0.5f * (a.y + b.y), 0.5f * (a.z + b.z));
+	float x = fminf(fmaxf((c.x - lo.x) * inv_extent.x, 0.0f), 1.0f);
+	float y = fminf(fmaxf((c.y - lo.y) * inv_extent.y, 0.0f), 1.0f);
+	float z = fminf(fmaxf((c.z - lo.z) * inv_extent.z, 0.0f), 1.0f);
+	unsigned int xi = min((unsigned int) (x * 1024.0f), 1023u);
+	unsigned int yi = min((unsigned int) (y * 1024.0f), 1023u);
+	unsigned int zi = min((unsigned int) (z * 1024.0f), 1023u);
+	unsigned int code = (spread10(xi) << 2) | (spread10(yi) << 1) | spread10(zi);
+	/* the index in the low word makes every key unique (Karras needs that) */
+	keys[i] = ((unsigned long long) code << 32) | (unsigned int) i;
+}
+
+__global__ void unpack_index_kernel(const unsigned long long *keys, int n, int *prim_index)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) prim_index[i] = (int) (unsigned int) (keys[i] & 0xffffffffull);
+}
+
+/* ---- Karras hierarchy ---------------------------------------------------- */
+
+__device__ __forceinline__ int delta(const unsigned long long *keys, int n, int i, int j)
+{
+	if (j < 0 || j >= n) return -1;
+	return __clzll((long long) (keys[i] ^ keys[j]));
+}
+
+/* children[2i], children[2i+1]: >= 0 internal, < 0 leaf (~slot).  parent[] is
+ * indexed by internal node i in [0,n-1) and by leaf slot s at (n-1)+s. */
+__global__ void hierarchy_kernel(const unsigned long long *keys, int n, int *children, int *parent)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n - 1) return;
+	int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+	int dmin = delta(keys, n, i, i - d);
+	int lmax = 2;
+	while (delta(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+	int l = 0;
+	for (int t = lmax / 2; t >= 1; t /= 2)
+		if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+	int j = i + l * d;
+	int dnode = delta(keys, n, i, j);
+	int s = 0;
+	for (int t = (l + 1) / 2; ; t = (t + 1) / 2) {
+		if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+		if (t == 1) break;
+	}
+	int gamma = i + s * d + min(d, 0);
+	int lo = min(i, j), hi = max(i, j);
+	int left = (lo == gamma) ? ~gamma : gamma;
+	int right = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
+	children[2 * i] = left;
+	children[2 * i + 1] = right;
+	parent[left >= 0 ? left : (n - 1) + ~left] = i;
+	parent[right >= 0 ? right : (n - 1) + ~right] = i;
+	if (i == 0) parent[0] = -1;
+}
+
+/* ---- padded leaf boxes ---------------------------------------------------- */
+
+__global__ void leaf_box_kernel(const float4 *A, const float4 *B, const int *prim_index, int n,
+                                double fuzz_r2, float cube_pad, float extra, float4 *leaf_lo, float4 *leaf_hi)
+{
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= n) return;
+	int p = prim_index[s];
+	float4 a = A[p], b = B[p];
+	float3 lo, hi;
+	int ty = __float_as_int(b.w);
+	if (ty == RT_OBJECT_SPHERE) {
+		/* a.w = r*r as the reference computes it (scene.c:112) */
+		float rp = (float) sqrt((double) fmaxf(a.w, 0.0f) + fuzz_r2);
+		rp = rp * 1.000001f + extra;
+		lo = make_float3(a.x - rp, a.y - rp, a.z - rp);
+		hi = make_float3(a.x + rp, a.y + rp, a.z + rp);
+	} else if (ty == RT_OBJECT_CUBE) {
+		float pad = cube_pad + extra;
+		lo = make_float3(fminf(a.x, b.x) - pad, fminf(a.y, b.y) - pad, fminf(a.z, b.z) - pad);
+		hi = make_float3(fmaxf(a.x, b.x) + pad, fmaxf(a.y, b.y) + pad, fmaxf(a.z, b.z) + pad);
+	} else {
+		/* unknown type never intersects (scene.c:138-153): empty box */
+		lo = make_float3(1.0f, 1.0f, 1.0f);
+		hi = make_float3(-1.0f, -1.0f, -1.0f);
+	}
+	leaf_lo[s] = make_float4(lo.x, lo.y, lo.z, 0.0f);
+	leaf_hi[s] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+}
+
+/* ---- bottom-up refit ------------------------------------------------------ */
+
+/* node_box[2i], node_box[2i+1] = lo/hi of internal node i (scratch) */
+__global__ void refit_kernel(const int *children, const int *parent, const float4 *leaf_lo, const float4 *leaf_hi,
+                             int n, unsigned int *visit, float4 *node_box, float4 *nodes)
+{
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= n) return;
+	int cur = parent[(n - 1) + s];
+	while (cur >= 0) {
+		/* the second thread to arrive owns the node: both subtrees are complete */
+		__threadfence();
+		if (atomicAdd(&visit[cur], 1u) == 0u) return;
+		__threadfence();
+		int cl = children[2 * cur], cr = children[2 * cur + 1];
+		float4 llo, lhi, rlo, rhi;
+		if (cl < 0) { llo = leaf_lo[~cl]; lhi = leaf_hi[~cl]; }
+		else { llo = __ldcg(&node_box[2 * cl]); lhi = __ldcg(&node_box[2 * cl + 1]); }
+		if (cr < 0) { rlo = leaf_lo[~cr]; rhi = leaf_hi[~cr]; }
+		else { rlo = __ldcg(&node_box[2 * cr]); rhi = __ldcg(&node_box[2 * cr + 1]); }
+		float4 *nd = nodes + 4 * (size_t) cur;
+		nd[0] = make_float4(llo.x, llo.y, llo.z, __int_as_float(cl));
+		nd[1] = make_float4(lhi.x, lhi.y, lhi.z, 0.0f);
+		nd[2] = make_float4(rlo.x, rlo.y, rlo.z, __int_as_float(cr));
+		nd[3] = make_float4(rhi.x, rhi.y, rhi.z, 0.0f);
+		/* union; an empty child box (lo > hi) is ignored */
+		bool le = llo.x > lhi.x, re = rlo.x > rhi.x;
+		float4 ulo, uhi;
+		if (le && re) { ulo = llo; uhi = lhi; }
+		else if (le) { ulo = rlo; uhi = rhi; }
+		else if (re) { ulo = llo; uhi = lhi; }
+		else {
+			ulo = make_float4(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z), 0.0f);
+			uhi = make_float4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), 0.0f);
+		}
+		__stcg(&node_box[2 * cur], ulo);
+		__stcg(&node_box[2 * cur + 1], uhi);
+		cur = parent[cur];
+	}
+}
+
+/* ---- host side ------------------------------------------------------------ */
+
+struct Scratch {
+	void *p = nullptr;
+	~Scratch() { cudaFree(p); }
+};
+
+static int *g_children_of(RtLbvh *bvh) { return bvh->parent + (2 * (size_t) bvh->num_prims - 1); }
+
+void rt_lbvh_free(RtLbvh *bvh)
+{
+	cudaFree(bvh->nodes); cudaFree(bvh->prim_index); cudaFree(bvh->parent);
+	cudaFree(bvh->leaf_lo); cudaFree(bvh->leaf_hi); cudaFree(bvh->visit);
+	*bvh = RtLbvh();
+}
+
+RtBvhView rt_lbvh_view(const RtLbvh *bvh)
+{
+	RtBvhView v;
+	v.nodes = bvh->nodes;
+	v.prim_index = bvh->prim_index;
+	v.num_prims = bvh->num_prims;
+	v.t_slack = bvh->t_slack;
+	return v;
+}
+
+float rt_lbvh_required_dmax(const RtLbvh *bvh, RtVector3 p)
+{
+	double dx = fmax(fabs((double) p.x - bvh->lo.x), fabs((double) p.x - bvh->hi.x));
+	double dy = fmax(fabs((double) p.y - bvh->lo.y), fabs((double) p.y - bvh->hi.y));
+	double dz = fmax(fabs((double) p.z - bvh->lo.z), fabs((double) p.z - bvh->hi.z));
+	return (float) sqrt(dx * dx + dy * dy + dz * dz);
+}
+
+int rt_lbvh_refit(RtLbvh *bvh, const float4 *geomA, const float4 *geomB, float d_max, cudaStream_t stream)
+{
+	int n = bvh->num_prims;
+	if (n <= 0) return RT_OK;
+	double D = (double) d_max;
+	double fuzz_r2 = RT_FUZZ_K * ldexp(1.0, -24) * D * D;
+	double mag = fmax(fmax(fabs((double) bvh->lo.x), fabs((double) bvh->hi.x)),
+	                  fmax(fmax(fabs((double) bvh->lo.y), fabs((double) bvh->hi.y)),
+	                       fmax(fabs((double) bvh->lo.z), fabs((double) bvh->hi.z))));
+	float cube_pad = (float) (ldexp(1.0, -20) * (mag + D));
+	float extra = (float) (ldexp(1.0, -18) * (mag + D));
+	int blocks = (n + 255) / 256;
+	leaf_box_kernel<<<blocks, 256, 0, stream>>>(geomA, geomB, bvh->prim_index, n, fuzz_r2, cube_pad, extra,
+	                                            bvh->leaf_lo, bvh->leaf_hi);
+	LCU(cudaGetLastError());
+	if (n >= 2) {
+		Scratch node_box;
+		LCU(cudaMalloc(&node_box.p, sizeof(float4) * 2 * (size_t) (n - 1)));
+		LCU(cudaMemsetAsync(bvh->visit, 0, sizeof(unsigned int) * (size_t) (n - 1), stream));
+		refit_kernel<<<blocks, 256, 0, stream>>>(g_children_of(bvh), bvh->parent, bvh->leaf_lo, bvh->leaf_hi, n,
+		                                         bvh->visit, (float4 *) node_box.p, bvh->nodes);
+		LCU(cudaGetLastError());
+		LCU(cudaStreamSynchronize(stream));
+	}
+	bvh->d_max = d_max;
+	bvh->t_slack = (float) (1e-3 * D);
+	return RT_OK;
+}
+
+int rt_lbvh_build(RtLbvh *bvh, const float4 *geomA, const float4 *geomB, int n,
+                  const RtPackedScene *hs, cudaStream_t stream)
+{
+	rt_lbvh_free(bvh);
+	if (n <= 0) return RT_OK;
+	bvh->num_prims = n;
+	bvh->lo = hs->bounds_lo;
+	bvh->hi = hs->bounds_hi;
+	size_t nn = (size_t) n;
+	LCU(cudaMalloc(&bvh->nodes, sizeof(float4) * 4 * (nn > 1 ? nn - 1 : 1)));
+	LCU(cudaMalloc(&bvh->prim_index, sizeof(int) * nn));
+	/* parent[0 .. 2n-1) followed by children[0 .. 2(n-1)) */
+	LCU(cudaMalloc(&bvh->parent, sizeof(int) * ((2 * nn - 1) + 2 * (nn > 1 ? nn - 1 : 1))));
+	LCU(cudaMalloc(&bvh->leaf_lo, sizeof(float4) * nn));
+	LCU(cudaMalloc(&bvh->leaf_hi, sizeof(float4) * nn));
+	LCU(cudaMalloc(&bvh->visit, sizeof(unsigned int) * (nn > 1 ? nn - 1 : 1)));
+
+	Scratch keys_in, keys_out, temp;
+	LCU(cudaMalloc(&keys_in.p, sizeof(unsigned long long) * nn));
+	LCU(cudaMalloc(&keys_out.p, sizeof(unsigned long long) * nn));
+
+	float3 lo = make_float3(hs->bounds_lo.x, hs->bounds_lo.y, hs->bounds_lo.z);
+	float3 ext = make_float3(hs->bounds_hi.x - lo.x, hs->bounds_hi.y - lo.y, hs->bounds_hi.z - lo.z);
+	float3 inv = make_float3(ext.x > 0 ? 1.0f / ext.x : 0.0f, ext.y > 0 ? 1.0f / ext.y : 0.0f,
+	                         ext.z > 0 ? 1.0f / ext.z : 0.0f);
+	int blocks = (n + 255) / 256;
+	morton_kernel<<<blocks, 256, 0, stream>>>(geomA, geomB, n, lo, inv, (unsigned long long *) keys_in.p);
+	LCU(cudaGetLastError());
+
+	size_t temp_bytes = 0;
+	LCU(cub::DeviceRadixSort::SortKeys(nullptr, temp_bytes, (const unsigned long long *) keys_in.p,
+	                                   (unsigned long long *) keys_out.p, n, 0, 64, stream));
+	LCU(cudaMalloc(&temp.p, temp_bytes ? temp_bytes : 4));
+	LCU(cub::DeviceRadixSort::SortKeys(temp.p, temp_bytes, (const unsigned long long *) keys_in.p,
+	                                   (unsigned long long *) keys_out.p, n, 0, 64, stream));
+	unpack_index_kernel<<<blocks, 256, 0, stream>>>((const unsigned long long *) keys_out.p, n, bvh->prim_index);
+	LCU(cudaGetLastError());
+	if (n >= 2) {
+		hierarchy_kernel<<<blocks, 256, 0, stream>>>((const unsigned long long *) keys_out.p, n,
+		                                             g_children_of(bvh), bvh->parent);
+		LCU(cudaGetLastError());
+	}
+	LCU(cudaStreamSynchronize(stream));
+
+	/* secondary rays start on surfaces, i.e. inside the primitive bounds: their
+	 * distance to any primitive is at most the bounds' diagonal.  The renderer
+	 * re-pads when the camera is farther than that (rt_api.cu). */
+	double dx = (double) ext.x, dy = (double) ext.y, dz = (double) ext.z;
+	float d_max = (float) (1.01 * sqrt(dx * dx + dy * dy + dz * dz) + 0.01);
+	return rt_lbvh_refit(bvh, geomA, geomB, d_max, stream);
+}

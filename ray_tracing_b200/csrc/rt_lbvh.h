@@ -1,0 +1,40 @@
+/*
+ * rt_lbvh.h -- device LBVH for scenes too large for the shared-memory linear
+ * scan (BASELINE.json config 5: 100 000 spheres).  The reference has no
+ * acceleration structure (scene.c:163 is an O(N) loop); the LBVH must return
+ * exactly what that loop returns, so it is built around the reference's
+ * *computed* intersection test, not the geometric primitives (see rt_lbvh.cu).
+ */
+#ifndef RT_LBVH_H
+#define RT_LBVH_H
+
+#include <cuda_runtime.h>
+#include "rt_host.h"
+#include "rt_params.h"
+
+struct RtLbvh {
+	float4 *nodes = nullptr;        /* 4 float4 per internal node (rt_params.h) */
+	int    *prim_index = nullptr;   /* Morton order -> primitive index */
+	int    *parent = nullptr;       /* internal-node parents; leaves at [n-1, 2n-1) */
+	float4 *leaf_lo = nullptr, *leaf_hi = nullptr;   /* padded primitive boxes, Morton order */
+	unsigned int *visit = nullptr;
+	int     num_prims = 0;
+	float   d_max = 0.0f;           /* largest origin-to-primitive distance the padding covers */
+	float   t_slack = 0.0f;
+	RtVector3 lo = {0, 0, 0}, hi = {0, 0, 0};   /* unpadded bounds of all primitives */
+};
+
+int  rt_lbvh_build(RtLbvh *bvh, const float4 *geomA, const float4 *geomB, int n,
+                   const RtPackedScene *host_scene, cudaStream_t stream);
+/* Re-pad and refit for ray origins up to `d_max` away from any primitive
+ * (topology unchanged).  Called when the camera leaves the region the build
+ * assumed. */
+int  rt_lbvh_refit(RtLbvh *bvh, const float4 *geomA, const float4 *geomB, float d_max, cudaStream_t stream);
+void rt_lbvh_free(RtLbvh *bvh);
+RtBvhView rt_lbvh_view(const RtLbvh *bvh);
+const char *rt_lbvh_last_error(void);
+
+/* distance from `p` to the farthest corner of the primitive bounds */
+float rt_lbvh_required_dmax(const RtLbvh *bvh, RtVector3 p);
+
+#endif

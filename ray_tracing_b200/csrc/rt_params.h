@@ -1,0 +1,79 @@
+/*
+ * rt_params.h -- kernel parameter blocks (POD, passed by value as
+ * __grid_constant__) shared by rt_api.cu and the two builds of rt_render.cu.
+ */
+#ifndef RT_PARAMS_H
+#define RT_PARAMS_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "rt_host.h"
+
+#define RT_BVH_STACK 64
+#define RT_TILE_W 8           /* a warp covers an 8x4 tile of low-res pixels */
+#define RT_TILE_H 4
+#define RT_BLOCK_THREADS 128
+#define RT_SMEM_MAX_OBJECTS 1024   /* linear-scan scenes are staged in shared memory */
+
+struct RtSceneView {
+	const float4 *geomA;      /* see rt_host.h for the record layout */
+	const float4 *geomB;
+	const float4 *mat;
+	int           n;
+	int           light_index;
+	RtVector3     light_pos;
+};
+
+struct RtSkyView {
+	const uchar4 *texels;     /* 6 faces, CubeFace order, RGBA8, row-major top row first */
+	int           w, h;
+	size_t        face_stride;/* w*h */
+};
+
+/*
+ * LBVH (Karras 2012) over primitive AABBs:
+ *   nodes[4*i + 0] = left  child box lo.xyz, .w = left child  (int bits)
+ *   nodes[4*i + 1] = left  child box hi.xyz
+ *   nodes[4*i + 2] = right child box lo.xyz, .w = right child (int bits)
+ *   nodes[4*i + 3] = right child box hi.xyz
+ * child >= 0: internal node index; child < 0: leaf, ~child = slot in the
+ * Morton-sorted order, prim_index[slot] = original primitive index.
+ */
+struct RtBvhView {
+	const float4 *nodes;
+	const int    *prim_index;
+	int           num_prims;
+	float         t_slack;    /* see rt_lbvh.cu: cull only if t_entry > best + slack */
+};
+
+struct RtRenderParams {
+	RtCameraFrame cam;
+	RtSceneView   scene;
+	RtBvhView     bvh;
+	RtSkyView     sky;
+	const float  *byte_lut;   /* 256 floats: (float)i/255 */
+
+	/* render_column geometry (main.c:278-296) */
+	int W, H, scale;
+	int num_columns, column_w;
+	int lw, lh;               /* W/scale, H/scale */
+	int cells_per_col;        /* ceil(column_w / scale): visible low-res pixels per column row */
+	int cells_per_row;        /* num_columns * cells_per_col */
+	int lrow0, lrow1;         /* low-res row band [lrow0, lrow1) rendered by this launch */
+	int tiles_x, tiles_y;     /* 8x4 tiles covering cells_per_row x (lrow1-lrow0) */
+	uint64_t pass_mix;        /* splitmix64(pass_index) */
+
+	/* output */
+	void  *fb;                /* RT_FB_F32X3: float[3] per pixel; RT_FB_U8X4: uchar4 */
+	int    fb_format;
+	int    fb_row_offset;     /* output row r is stored at fb row (r - fb_row_offset) */
+	float *accum;             /* optional W*H*3 accumulation buffer (row offset applies too) */
+	int    accum_row_offset;
+	float  accum_weight;      /* 1.0f/(scale*scale)  (main.c:278,394) */
+	float  inv_count;         /* 1.0f/accum_count after this pass (main.c:476) */
+
+	unsigned long long *ray_counter;
+	unsigned int       *work_counter;   /* persistent kernel: next tile-ordered pixel */
+};
+
+#endif

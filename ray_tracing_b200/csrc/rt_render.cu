@@ -1,0 +1,389 @@
+/*
+ * rt_render.cu -- the render kernels (sm_100a).  Compiled twice, see
+ * rt_device.cuh: -DRT_NS=rt_exact -fmad=false and -DRT_NS=rt_fast -fmad=true.
+ *
+ * Replaces: worker()/render_column()/pixel() (src/main.c:131-414) -- the
+ * pthread-per-column pool becomes one launch over low-res pixels.
+ *
+ * Two kernels, same device functions:
+ *   render_pixel_kernel       one thread per low-res pixel, 8x4 pixel tile per
+ *                             warp, each thread runs its whole path;
+ *   render_persistent_kernel  resident warps; a lane whose path ended stores
+ *                             its pixel and immediately starts the next pixel
+ *                             of the warp's batch, so the convergent
+ *                             nearest-hit scan keeps all 32 lanes busy while
+ *                             paths are 1..40 rays long (SURVEY.md 8(a)
+ *                             divergence data).
+ * Scenes up to RT_SMEM_MAX_OBJECTS are scanned linearly from shared memory
+ * (every lane reads the same primitive: broadcast, no bank conflicts); larger
+ * ones walk the LBVH in global memory.
+ */
+#include "rt_device.cuh"
+
+namespace RT_NS {
+
+/* ---------------------------------------------------------------- helpers */
+
+struct SharedScene {
+	float4 *A;
+	float4 *B;
+	float  *lut;
+};
+
+__device__ __forceinline__ SharedScene stage_scene(const RtRenderParams &P, unsigned char *smem, bool linear)
+{
+	SharedScene s;
+	s.lut = reinterpret_cast<float *>(smem);
+	s.A = reinterpret_cast<float4 *>(smem + 256 * sizeof(float));
+	s.B = s.A + (linear ? P.scene.n : 0);
+	for (int i = threadIdx.x; i < 256; i += blockDim.x) s.lut[i] = __ldg(&P.byte_lut[i]);
+	if (linear)
+		for (int i = threadIdx.x; i < P.scene.n; i += blockDim.x) {
+			s.A[i] = __ldg(&P.scene.geomA[i]);
+			s.B[i] = __ldg(&P.scene.geomB[i]);
+		}
+	__syncthreads();
+	return s;
+}
+
+/* tile-ordered work index -> low-res cell (cx, cy) inside the band */
+__device__ __forceinline__ bool cell_of(const RtRenderParams &P, unsigned idx, int &cx, int &cy)
+{
+	unsigned tile = idx >> 5, lane = idx & 31;
+	int tx = (int) (tile % (unsigned) P.tiles_x), ty = (int) (tile / (unsigned) P.tiles_x);
+	cx = tx * RT_TILE_W + (int) (lane & (RT_TILE_W - 1));
+	cy = ty * RT_TILE_H + (int) (lane / RT_TILE_W);
+	return cx < P.cells_per_row && cy < (P.lrow1 - P.lrow0);
+}
+
+struct Cell {
+	int   x0, y0;     /* first output pixel of the tile */
+	int   tw;         /* tile width after column clipping (main.c:302-303) */
+	float u, v;
+};
+
+/* main.c:280-303 */
+__device__ __forceinline__ Cell cell_geometry(const RtRenderParams &P, int cx, int cy)
+{
+	Cell c;
+	int col = cx / P.cells_per_col;
+	int i = cx - col * P.cells_per_col;
+	int j = P.lrow0 + cy;
+	int column_x = P.column_w * col;
+	int lcx = column_x / P.scale;
+	float u = (float) (lcx + i) / (float) (P.lw - 1);
+	float v = (float) j / (float) (P.lh - 1);
+	c.u = 1.0f - u;
+	c.v = 1.0f - v;
+	c.x0 = column_x + i * P.scale;
+	c.y0 = j * P.scale;
+	c.tw = min(P.scale, P.column_w - i * P.scale);
+	return c;
+}
+
+/* main.c:305-310 (tile replication) fused with main.c:394 (accumulate) and
+ * main.c:476 (resolve) when an accumulation buffer is attached. */
+__device__ __forceinline__ void store_cell(const RtRenderParams &P, const Cell &c, f3 color)
+{
+	for (int g = 0; g < P.scale; g++) {
+		int y = c.y0 + g;
+		for (int t = 0; t < c.tw; t++) {
+			int x = c.x0 + t;
+			f3 out = color;
+			if (P.accum) {
+				float *a = P.accum + 3 * ((size_t) (y - P.accum_row_offset) * P.W + x);
+				f3 acc = mk(a[0] + color.x * P.accum_weight, a[1] + color.y * P.accum_weight,
+				            a[2] + color.z * P.accum_weight);
+				a[0] = acc.x; a[1] = acc.y; a[2] = acc.z;
+				out = scl3(acc, P.inv_count);
+			}
+			size_t p = (size_t) (y - P.fb_row_offset) * P.W + x;
+			if (P.fb_format == RT_FB_F32X3) {
+				float *f = reinterpret_cast<float *>(P.fb) + 3 * p;
+				f[0] = out.x; f[1] = out.y; f[2] = out.z;
+			} else {
+				/* main.c:666-670: (uint8_t)(x*255) */
+				uchar4 q;
+				q.x = (unsigned char) __float2uint_rz(out.x * 255.0f);
+				q.y = (unsigned char) __float2uint_rz(out.y * 255.0f);
+				q.z = (unsigned char) __float2uint_rz(out.z * 255.0f);
+				q.w = 255;
+				reinterpret_cast<uchar4 *>(P.fb)[p] = q;
+			}
+		}
+	}
+}
+
+__device__ __forceinline__ void count_rays(const RtRenderParams &P, unsigned rays)
+{
+	for (int o = 16; o > 0; o >>= 1) rays += __shfl_xor_sync(0xffffffffu, rays, o);
+	if ((threadIdx.x & 31) == 0 && rays) atomicAdd(P.ray_counter, (unsigned long long) rays);
+}
+
+/* One trace + state transition for the lane's path. */
+template <bool LBVH>
+__device__ __forceinline__ void path_step(Path &p, const RtRenderParams &P, const SharedScene &S)
+{
+	f3 dn = unit3(p.ray_d);                 /* scene.c:158 */
+	RayQ q = ray_quadratic(dn);
+	Hit h;
+	if (LBVH) h = nearest_lbvh(P.bvh, P.scene.geomA, P.scene.geomB, p.ray_o, dn, q);
+	else      h = nearest_linear(S.A, S.B, P.scene.n, p.ray_o, dn, q);
+	f3 ro = p.ray_o;
+	path_advance(p, h, dn, P.scene, P.sky, S.lut,
+	             [&](const Hit &hh, f3 d, f3 &point, f3 &normal) {
+		             if (LBVH) surface_of(hh, __ldg(&P.scene.geomA[hh.obj]), __ldg(&P.scene.geomB[hh.obj]), ro, d, point, normal);
+		             else      surface_of(hh, S.A[hh.obj], S.B[hh.obj], ro, d, point, normal);
+	             });
+}
+
+/* ---------------------------------------------------------------- kernels */
+
+template <bool LBVH>
+__global__ void __launch_bounds__(RT_BLOCK_THREADS)
+render_pixel_kernel(const __grid_constant__ RtRenderParams P)
+{
+	extern __shared__ __align__(16) unsigned char smem[];
+	SharedScene S = stage_scene(P, smem, !LBVH);
+
+	unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned rays = 0;
+	int cx, cy;
+	if (idx < (unsigned) (P.tiles_x * P.tiles_y) * 32u && cell_of(P, idx, cx, cy)) {
+		Cell c = cell_geometry(P, cx, cy);
+		Path p;
+		path_begin(p, P.cam, c.u, c.v, P.pass_mix);
+		while (p.alive) {
+			path_step<LBVH>(p, P, S);
+			rays++;
+		}
+		store_cell(P, c, path_final(p));
+	}
+	count_rays(P, rays);
+}
+
+#define RT_WARP_BATCH 8     /* tiles (of 32 pixels) a warp claims per global atomic */
+
+template <bool LBVH>
+__global__ void __launch_bounds__(RT_BLOCK_THREADS)
+render_persistent_kernel(const __grid_constant__ RtRenderParams P)
+{
+	extern __shared__ __align__(16) unsigned char smem[];
+	SharedScene S = stage_scene(P, smem, !LBVH);
+
+	const unsigned full = 0xffffffffu;
+	const unsigned lane = threadIdx.x & 31;
+	const unsigned total = (unsigned) (P.tiles_x * P.tiles_y) * 32u;
+
+	Path p;
+	p.alive = false;
+	Cell c;
+	bool owns = false;          /* lane holds a pixel whose path is running or just ended */
+	unsigned rays = 0;
+	unsigned batch_next = 0, batch_end = 0;   /* warp-uniform: tile-ordered pixel indices */
+	bool exhausted = false;                   /* warp-uniform */
+
+	for (;;) {
+		unsigned idle = __ballot_sync(full, !p.alive);
+		if (idle) {
+			if (!p.alive && owns) {
+				store_cell(P, c, path_final(p));
+				owns = false;
+			}
+			if (batch_next == batch_end && !exhausted) {
+				unsigned base = 0;
+				if (lane == 0) base = atomicAdd(P.work_counter, RT_WARP_BATCH * 32u);
+				base = __shfl_sync(full, base, 0);
+				if (base >= total) exhausted = true;
+				else { batch_next = base; batch_end = min(base + RT_WARP_BATCH * 32u, total); }
+			}
+			/* hand the idle lanes the next pixels of the warp's batch */
+			unsigned avail = batch_end - batch_next;
+			unsigned rank = __popc(idle & ((1u << lane) - 1u));
+			int cx, cy;
+			if (!p.alive && rank < avail && cell_of(P, batch_next + rank, cx, cy)) {
+				c = cell_geometry(P, cx, cy);
+				path_begin(p, P.cam, c.u, c.v, P.pass_mix);
+				owns = true;
+			}
+			batch_next += min((unsigned) __popc(idle), avail);
+		}
+		if (__ballot_sync(full, p.alive) == 0) {
+			if (exhausted && batch_next == batch_end) break;
+			continue;       /* only clipped cells were handed out; fetch more */
+		}
+		if (p.alive) {
+			path_step<LBVH>(p, P, S);
+			rays++;
+		}
+	}
+	count_rays(P, rays);
+}
+
+/* ------------------------------------------------------------ unit probes */
+
+template <bool LBVH>
+__global__ void probe_trace_kernel(RtRenderParams P, const float *rays6, int n, float *out7, int *obj)
+{
+	extern __shared__ __align__(16) unsigned char smem[];
+	SharedScene S = stage_scene(P, smem, !LBVH);
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	f3 o = mk(rays6[6 * i], rays6[6 * i + 1], rays6[6 * i + 2]);
+	f3 d = unit3(mk(rays6[6 * i + 3], rays6[6 * i + 4], rays6[6 * i + 5]));
+	RayQ q = ray_quadratic(d);
+	Hit h;
+	if (LBVH) h = nearest_lbvh(P.bvh, P.scene.geomA, P.scene.geomB, o, d, q);
+	else      h = nearest_linear(S.A, S.B, P.scene.n, o, d, q);
+	float *r = out7 + 7 * (size_t) i;
+	obj[i] = h.obj;
+	if (h.obj < 0) {                        /* scene.c:175-181 */
+		r[0] = -1.0f;
+		for (int k = 1; k < 7; k++) r[k] = 0.0f;
+		return;
+	}
+	f3 pt, nm;
+	surface_of(h, __ldg(&P.scene.geomA[h.obj]), __ldg(&P.scene.geomB[h.obj]), o, d, pt, nm);
+	r[0] = h.t;
+	r[1] = pt.x; r[2] = pt.y; r[3] = pt.z;
+	r[4] = nm.x; r[5] = nm.y; r[6] = nm.z;
+}
+
+__global__ void probe_sky_kernel(RtSkyView sky, const float *lut, const float *dirs3, int n, float *out3)
+{
+	__shared__ float s_lut[256];
+	for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = lut[i];
+	__syncthreads();
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	f3 c = sky_lookup(sky, s_lut, mk(dirs3[3 * i], dirs3[3 * i + 1], dirs3[3 * i + 2]));
+	out3[3 * i] = c.x; out3[3 * i + 1] = c.y; out3[3 * i + 2] = c.z;
+}
+
+__global__ void probe_camera_kernel(RtCameraFrame cam, const float *pxpy, int n, float *rays6)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	f3 d = camera_dir(cam, pxpy[2 * i], pxpy[2 * i + 1]);
+	float *r = rays6 + 6 * (size_t) i;
+	r[0] = cam.origin.x; r[1] = cam.origin.y; r[2] = cam.origin.z;
+	r[3] = d.x; r[4] = d.y; r[5] = d.z;
+}
+
+__global__ void probe_rng_kernel(uint64_t state, int n, uint64_t *u64_out, float *f32_out, float *dir_out)
+{
+	if (blockIdx.x || threadIdx.x) return;
+	uint64_t s = state;
+	if (u64_out) for (int i = 0; i < n; i++) u64_out[i] = wyhash64(s);
+	s = state;
+	if (f32_out) for (int i = 0; i < n; i++) f32_out[i] = random_float(s);
+	s = state;
+	if (dir_out) for (int i = 0; i < n; i++) {
+		f3 d = random_direction(s);
+		dir_out[3 * i] = d.x; dir_out[3 * i + 1] = d.y; dir_out[3 * i + 2] = d.z;
+	}
+}
+
+} // namespace RT_NS
+
+/* ------------------------------------------------------------ launchers */
+
+#define RT_CAT2(a, b) a##_##b
+#define RT_CAT(a, b) RT_CAT2(a, b)
+#define RT_FN(name) RT_CAT(RT_NS, name)
+
+static size_t smem_bytes(const RtRenderParams &P, bool lbvh)
+{
+	return 256 * sizeof(float) + (lbvh ? 0 : 2 * sizeof(float4) * (size_t) P.scene.n);
+}
+
+template <class K>
+static cudaError_t allow_smem(K kernel, size_t bytes)
+{
+	if (bytes <= 48 * 1024) return cudaSuccess;
+	return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+}
+
+extern "C" cudaError_t RT_FN(launch_render)(const RtRenderParams *P, int lbvh, int persistent,
+                                             int grid_blocks, cudaStream_t stream)
+{
+	using namespace RT_NS;
+	size_t sm = smem_bytes(*P, lbvh != 0);
+	unsigned total = (unsigned) (P->tiles_x * P->tiles_y) * 32u;
+	if (total == 0) return cudaSuccess;
+	cudaError_t e;
+	if (persistent) {
+		if (lbvh) {
+			if ((e = allow_smem(render_persistent_kernel<true>, sm)) != cudaSuccess) return e;
+			render_persistent_kernel<true><<<grid_blocks, RT_BLOCK_THREADS, sm, stream>>>(*P);
+		} else {
+			if ((e = allow_smem(render_persistent_kernel<false>, sm)) != cudaSuccess) return e;
+			render_persistent_kernel<false><<<grid_blocks, RT_BLOCK_THREADS, sm, stream>>>(*P);
+		}
+	} else {
+		unsigned blocks = (total + RT_BLOCK_THREADS - 1) / RT_BLOCK_THREADS;
+		if (lbvh) {
+			if ((e = allow_smem(render_pixel_kernel<true>, sm)) != cudaSuccess) return e;
+			render_pixel_kernel<true><<<blocks, RT_BLOCK_THREADS, sm, stream>>>(*P);
+		} else {
+			if ((e = allow_smem(render_pixel_kernel<false>, sm)) != cudaSuccess) return e;
+			render_pixel_kernel<false><<<blocks, RT_BLOCK_THREADS, sm, stream>>>(*P);
+		}
+	}
+	return cudaGetLastError();
+}
+
+/* occupancy query for sizing the persistent grid */
+extern "C" cudaError_t RT_FN(persistent_blocks_per_sm)(const RtRenderParams *P, int lbvh, int *out)
+{
+	using namespace RT_NS;
+	size_t sm = smem_bytes(*P, lbvh != 0);
+	cudaError_t e;
+	if (lbvh) {
+		if ((e = allow_smem(render_persistent_kernel<true>, sm)) != cudaSuccess) return e;
+		return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, render_persistent_kernel<true>, RT_BLOCK_THREADS, sm);
+	}
+	if ((e = allow_smem(render_persistent_kernel<false>, sm)) != cudaSuccess) return e;
+	return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, render_persistent_kernel<false>, RT_BLOCK_THREADS, sm);
+}
+
+extern "C" cudaError_t RT_FN(launch_probe_trace)(const RtRenderParams *P, int lbvh, const float *rays6, int n,
+                                                  float *out7, int *obj, cudaStream_t stream)
+{
+	using namespace RT_NS;
+	if (n <= 0) return cudaSuccess;
+	size_t sm = smem_bytes(*P, lbvh != 0);
+	int blocks = (n + 127) / 128;
+	cudaError_t e;
+	if (lbvh) {
+		if ((e = allow_smem(probe_trace_kernel<true>, sm)) != cudaSuccess) return e;
+		probe_trace_kernel<true><<<blocks, 128, sm, stream>>>(*P, rays6, n, out7, obj);
+	} else {
+		if ((e = allow_smem(probe_trace_kernel<false>, sm)) != cudaSuccess) return e;
+		probe_trace_kernel<false><<<blocks, 128, sm, stream>>>(*P, rays6, n, out7, obj);
+	}
+	return cudaGetLastError();
+}
+
+extern "C" cudaError_t RT_FN(launch_probe_sky)(const RtSkyView *sky, const float *lut, const float *dirs3, int n,
+                                                float *out3, cudaStream_t stream)
+{
+	if (n <= 0) return cudaSuccess;
+	RT_NS::probe_sky_kernel<<<(n + 127) / 128, 128, 0, stream>>>(*sky, lut, dirs3, n, out3);
+	return cudaGetLastError();
+}
+
+extern "C" cudaError_t RT_FN(launch_probe_camera)(const RtCameraFrame *cam, const float *pxpy, int n,
+                                                   float *rays6, cudaStream_t stream)
+{
+	if (n <= 0) return cudaSuccess;
+	RT_NS::probe_camera_kernel<<<(n + 127) / 128, 128, 0, stream>>>(*cam, pxpy, n, rays6);
+	return cudaGetLastError();
+}
+
+extern "C" cudaError_t RT_FN(launch_probe_rng)(uint64_t state, int n, uint64_t *u64_out, float *f32_out,
+                                                float *dir_out, cudaStream_t stream)
+{
+	RT_NS::probe_rng_kernel<<<1, 32, 0, stream>>>(state, n, u64_out, f32_out, dir_out);
+	return cudaGetLastError();
+}
