@@ -1,0 +1,368 @@
+"""Parity tests proper: the CUDA path, called through the C ABI
+(libraytrace_b200.so), against the oracle on the same seeded inputs, against
+the committed golden vectors (outputs of the unmodified reference), and
+through size-independent properties at BASELINE.json's full sizes.
+
+Bar (BASELINE.json north_star): the exact variant (-fmad=false) is bit-exact;
+the fast variant differs by at most 1 LSB per 8-bit channel (main.c:666-670
+quantisation) on >= 99.9 % of pixels.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, random_scene
+from ray_tracing_b200 import host, scenes
+from ray_tracing_b200.host import (RT_FB_U8X4, RT_KERNEL_PERSISTENT, RT_KERNEL_PIXEL, RT_TRAVERSAL_LBVH,
+                                   RT_TRAVERSAL_LINEAR, RT_VARIANT_EXACT, RT_VARIANT_FAST, Camera)
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = [RT_KERNEL_PIXEL, RT_KERNEL_PERSISTENT]
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(GOLDEN, "reference_vectors.npz"))
+
+
+# ------------------------------------------------------------------ probes
+
+
+def test_native_library_is_loaded(renderer):
+    maps = open("/proc/self/maps").read()
+    assert "libraytrace_b200.so" in maps
+    assert renderer.num_gpus == 1
+
+
+def test_rng_matches_oracle_and_golden(renderer, port, gold):
+    u, f = renderer.debug_rng(0, 8)
+    assert [int(x) for x in u] == [int(x) for x in gold["rng_u64_state0"]]
+    assert np.array_equal(bits(f), bits(gold["rng_f32_state0"]))
+    for st in (1, 0xDEADBEEF, 2**63 + 5):
+        u, f = renderer.debug_rng(st, 64)
+        assert [int(x) for x in u] == port.rng_u64(st, 64)
+        assert np.array_equal(bits(f), bits(port.random_floats(st, 64)))
+        d = renderer.debug_random_directions(st, 1)[0]
+        assert np.array_equal(bits(d), bits(port.random_direction(st)[0]))
+    assert host.pixel_key(0.25, 0.75, 3) == port.pixel_key(0.25, 0.75, 3)
+
+
+def test_camera_rays_match_oracle_and_golden(renderer, port, gold):
+    got = renderer.debug_camera_rays(Camera(), gold["camera_pxpy"], 1280 / 720)
+    assert np.array_equal(bits(got), bits(gold["camera_rays_16x9"]))
+    rng = np.random.default_rng(1)
+    for _ in range(10):
+        cam = Camera(tuple(rng.uniform(-5, 5, 3)), tuple(rng.normal(size=3)), (0, 1, 0), float(rng.uniform(10, 80)))
+        pts = rng.uniform(0, 1, (64, 2)).astype(np.float32)
+        got = renderer.debug_camera_rays(cam, pts, 1.6)
+        want = np.stack([port.camera_ray(px, py, 1.6, cam.as_dict()) for px, py in pts])
+        assert np.array_equal(bits(got), bits(want))
+
+
+def test_cubemap_matches_oracle_and_golden(renderer, port, gold, small_sky):
+    renderer.upload_skybox(small_sky)
+    assert np.array_equal(bits(renderer.debug_sample_cubemap(gold["sky_dirs"])), bits(gold["sky_colors"]))
+    rng = np.random.default_rng(3)
+    dirs = rng.normal(size=(20000, 3)).astype(np.float32)
+    dirs[:100, 0] = dirs[:100, 1]
+    dirs[100:200, 2] = -dirs[100:200, 0]
+    dirs[210:220, :2] = 0.0
+    assert np.array_equal(bits(renderer.debug_sample_cubemap(dirs)), bits(port.sample_cubemap_many(small_sky, dirs)))
+
+
+def test_trace_matches_golden(renderer, gold):
+    objs = np.frombuffer(gold["scene0_objects"].tobytes(), dtype=host.OBJECT_DTYPE)
+    renderer.upload_scene(objs)
+    for variant in (RT_VARIANT_EXACT,):
+        hit, obj = renderer.debug_trace(gold["trace_rays"], variant=variant)
+        assert np.array_equal(obj, gold["trace_obj"])
+        assert np.array_equal(bits(hit), bits(gold["trace_hits"]))
+
+
+@pytest.mark.parametrize("seed,n,spheres", [(0, 40, False), (1, 200, True), (2, 1024, False)])
+def test_trace_random_scenes_linear_and_lbvh(renderer, port, seed, n, spheres):
+    objs = random_scene(n, seed, spheres_only=spheres)
+    renderer.upload_scene(objs)
+    rng = np.random.default_rng(seed + 100)
+    m = 20000
+    rays = np.concatenate([rng.uniform(-8, 8, (m, 3)), rng.normal(size=(m, 3))], axis=1).astype(np.float32)
+    tgt = objs["geom"][rng.integers(0, n, m // 2), :3] + rng.normal(scale=0.3, size=(m // 2, 3))
+    rays[m // 2:, 3:] = tgt - rays[m // 2:, :3]
+    rays[:50, 3:] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, 50)] * rng.choice([-1, 1], (50, 1))
+    rays[50:60, 3:] = 1e-7
+    rays[60:70, 4] = 0.0
+    want_hit, want_obj = port.trace_many(objs, rays)
+    hit, obj = renderer.debug_trace(rays, traversal=RT_TRAVERSAL_LINEAR)
+    assert np.array_equal(obj, want_obj)
+    assert np.array_equal(bits(hit), bits(want_hit))
+    if n > host.RT_LBVH_THRESHOLD:
+        hit, obj = renderer.debug_trace(rays, traversal=RT_TRAVERSAL_LBVH)
+        assert np.array_equal(obj, want_obj)
+        assert np.array_equal(bits(hit), bits(want_hit))
+
+
+# ------------------------------------------------------------------ frames
+
+GOLD_CASES = [
+    ("scene0_96x54_s1", 0, 96, 54, 1, 1, 0),
+    ("scene1_96x54_s1", 1, 96, 54, 1, 1, 0),
+    ("scene2_96x54_s1", 2, 96, 54, 1, 1, 0),
+    ("scene0_128x72_s2_c4_p3", 0, 128, 72, 2, 4, 3),
+    ("scene0_100x60_s4_c3", 0, 100, 60, 4, 3, 0),
+    ("scene1_120x68_s16_c1_p1", 1, 120, 68, 16, 1, 1),
+]
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("name,sc,W,H,s,T,p", GOLD_CASES)
+def test_frames_equal_reference_golden(renderer, gold, small_sky, builtin_objects, kernel, name, sc, W, H, s, T, p):
+    renderer.upload_skybox(small_sky)
+    renderer.upload_scene(builtin_objects[sc])
+    frame, st = renderer.render_frame(Camera(), W, H, s, num_columns=T, pass_index=p, kernel=kernel)
+    assert np.array_equal(bits(frame), bits(gold[name])), name
+    assert st["rays"] > 0 and st["render_ms"] > 0
+
+
+def test_moved_camera_golden(renderer, gold, small_sky, builtin_objects):
+    c = gold["moved_camera"]
+    cam = Camera(tuple(c[0:3]), tuple(c[3:6]), tuple(c[6:9]), float(c[9]))
+    renderer.upload_skybox(small_sky)
+    renderer.upload_scene(builtin_objects[0])
+    frame, _ = renderer.render_frame(cam, 96, 54, 1)
+    assert np.array_equal(bits(frame), bits(gold["scene0_96x54_moved"]))
+
+
+@pytest.mark.parametrize("sc", [0, 1, 2])
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_720p_bit_exact_vs_oracle(renderer, port, real_sky, builtin_objects, sc, kernel):
+    """BASELINE.json config 1 size (1280x720, scale 1, default pose)."""
+    renderer.upload_skybox(real_sky)
+    renderer.upload_scene(builtin_objects[sc])
+    frame, st = renderer.render_frame(Camera(), 1280, 720, 1, kernel=kernel)
+    want, rays = port.render(port.world(builtin_objects[sc], real_sky), 1280, 720, 1, 1, 0)
+    assert np.array_equal(bits(frame), bits(want))
+    assert st["rays"] == rays
+    assert st["pixels"] == 1280 * 720
+
+
+@pytest.mark.parametrize("sc", [1, 2])
+def test_1080p_bit_exact_vs_oracle(renderer, port, real_sky, builtin_objects, sc):
+    """BASELINE.json config 2 (scene_1 / scene_2 at 1920x1080)."""
+    renderer.upload_skybox(real_sky)
+    renderer.upload_scene(builtin_objects[sc])
+    frame, st = renderer.render_frame(Camera(), 1920, 1080, 1)
+    want, rays = port.render(port.world(builtin_objects[sc], real_sky), 1920, 1080, 1, 1, 0)
+    assert np.array_equal(bits(frame), bits(want))
+    assert st["rays"] == rays
+
+
+@pytest.mark.parametrize("W,H,s,T,p", [(161, 91, 2, 3, 5), (200, 120, 8, 4, 1), (192, 108, 16, 2, 0), (1920, 1080, 16, 1, 2), (333, 77, 1, 7, 9)])
+def test_scales_columns_passes_vs_oracle(renderer, port, small_sky, builtin_objects, W, H, s, T, p):
+    renderer.upload_skybox(small_sky)
+    renderer.upload_scene(builtin_objects[0])
+    world = port.world(builtin_objects[0], small_sky)
+    want, rays = port.render(world, W, H, s, T, p)
+    for kernel in KERNELS:
+        frame, st = renderer.render_frame(Camera(), W, H, s, num_columns=T, pass_index=p, kernel=kernel)
+        assert np.array_equal(bits(frame), bits(want))
+        assert st["rays"] == rays
+
+
+def test_random_scene_random_camera(renderer, port, small_sky):
+    objs = random_scene(60, 11)
+    cam = Camera((7.5, 4.0, 9.0), (-0.7, -0.3, -0.8), (0, 1, 0), 30.0)
+    renderer.upload_skybox(small_sky)
+    renderer.upload_scene(objs)
+    frame, st = renderer.render_frame(cam, 320, 200, 1, pass_index=2)
+    want, rays = port.render(port.world(objs, small_sky, cam.as_dict()), 320, 200, 1, 1, 2)
+    assert np.array_equal(bits(frame), bits(want))
+    assert st["rays"] == rays
+
+
+def test_north_star_entry_point(renderer, port, small_sky, builtin_objects):
+    renderer.upload_skybox(small_sky)
+    frame = renderer.render_frame_simple(builtin_objects[1], Camera(), 160, 90, 2)
+    want, _ = port.render(port.world(builtin_objects[1], small_sky), 160, 90, 2, 1, 0)
+    assert np.array_equal(bits(frame), bits(want))
+    # scene == NULL reuses the upload
+    again = renderer.render_frame_simple(None, Camera(), 160, 90, 2)
+    assert np.array_equal(bits(again), bits(want))
+
+
+def test_edge_cases(renderer, port, small_sky):
+    renderer.upload_skybox(small_sky)
+    # empty scene: every pixel is sky
+    empty = np.zeros(0, host.OBJECT_DTYPE)
+    renderer.upload_scene(empty)
+    frame, st = renderer.render_frame(Camera(), 64, 36, 1)
+    want, rays = port.render(port.world(empty, small_sky), 64, 36, 1, 1, 0)
+    assert np.array_equal(bits(frame), bits(want)) and st["rays"] == rays == 64 * 36
+    # camera inside a box ignores that box (scene.c:67 returns tnear < 0)
+    box = host.parse_scene_string("cube origin {4 4 4} size {2 2 2}\nsphere center {0 0 0} radius 1")
+    renderer.upload_scene(box)
+    frame, _ = renderer.render_frame(Camera(), 64, 36, 1)
+    want, _ = port.render(port.world(box, small_sky), 64, 36, 1, 1, 0)
+    assert np.array_equal(bits(frame), bits(want))
+    # a 1024-object scene (MAX_OBJECTS) through both traversals
+    objs = random_scene(1024, 5)
+    renderer.upload_scene(objs)
+    want, rays = port.render(port.world(objs, small_sky), 96, 54, 1, 1, 0)
+    for trav in (RT_TRAVERSAL_LINEAR, RT_TRAVERSAL_LBVH):
+        frame, st = renderer.render_frame(Camera(), 96, 54, 1, traversal=trav)
+        assert np.array_equal(bits(frame), bits(want)) and st["rays"] == rays
+    # bad arguments are reported, not aborted on
+    with pytest.raises(host.RtError):
+        renderer.render_frame(Camera(), 64, 36, 0)
+    with pytest.raises(host.RtError):
+        renderer.render_frame(Camera(), 64, 36, 2, rows=(3, 20))
+
+
+def test_fast_variant_within_tolerance(renderer, port, real_sky, builtin_objects):
+    """FMA-contracted build: <= 1 LSB per 8-bit channel on >= 99.9 % of pixels."""
+    renderer.upload_skybox(real_sky)
+    for sc in (0, 1, 2):
+        renderer.upload_scene(builtin_objects[sc])
+        exact, _ = renderer.render_frame(Camera(), 1280, 720, 1, variant=RT_VARIANT_EXACT)
+        fast, _ = renderer.render_frame(Camera(), 1280, 720, 1, variant=RT_VARIANT_FAST)
+        qa = host.quantize_frame(exact).astype(np.int32)
+        qb = host.quantize_frame(fast).astype(np.int32)
+        ok = (np.abs(qa - qb).max(axis=-1) <= 1).mean()
+        assert ok >= 0.999, (sc, ok)
+
+
+def test_u8x4_framebuffer(renderer, small_sky, builtin_objects):
+    renderer.upload_skybox(small_sky)
+    renderer.upload_scene(builtin_objects[0])
+    f32, _ = renderer.render_frame(Camera(), 160, 90, 1)
+    u8, _ = renderer.render_frame(Camera(), 160, 90, 1, fb_format=RT_FB_U8X4)
+    assert np.array_equal(u8[..., :3], host.quantize_frame(f32))
+    assert (u8[..., 3] == 255).all()
+
+
+# ------------------------------------------------- accumulate / sweep (R12)
+
+
+def test_progressive_sweep_vs_oracle(renderer, port, small_sky, builtin_objects):
+    """BASELINE.json config 4 semantics at a small size, plus 1080p below."""
+    W, H = 192, 108          # 108 % 16 = 12: rows the scale-16 pass never writes
+    renderer.upload_skybox(small_sky)
+    renderer.upload_scene(builtin_objects[0])
+    world = port.world(builtin_objects[0], small_sky)
+    frame, st = renderer.render_sweep(Camera(), W, H, 16, first_pass=0)
+    acc = np.zeros((H, W, 3), np.float32)
+    count = np.float32(0)
+    rays = 0
+    for p, s in enumerate((16, 8, 4, 2, 1)):
+        data, r = port.render(world, W, H, s, 1, p)
+        rays += r
+        port.accumulate(acc, data, s)
+        count = np.float32(count + np.float32(1.0) / np.float32(s * s))
+    want = port.resolve(acc, count)
+    assert np.array_equal(bits(frame), bits(want))
+    assert st["rays"] == rays
+    assert renderer.accum_count() == count
+    # continuing at scale 1 keeps averaging (workers stay at scale 1, main.c:402)
+    frame2, _ = renderer.render_frame(Camera(), W, H, 1, pass_index=5, accumulate=1)
+    data, _ = port.render(world, W, H, 1, 1, 5)
+    port.accumulate(acc, data, 1)
+    count = np.float32(count + np.float32(1))
+    assert np.array_equal(bits(frame2), bits(port.resolve(acc, count)))
+    renderer.accum_reset()
+    assert renderer.accum_count() == 0.0
+
+
+def test_sweep_1080p_vs_oracle(renderer, port, real_sky, builtin_objects):
+    W, H = 1920, 1080
+    renderer.upload_skybox(real_sky)
+    renderer.upload_scene(builtin_objects[0])
+    world = port.world(builtin_objects[0], real_sky)
+    frame, st = renderer.render_sweep(Camera(), W, H, 16, first_pass=0)
+    acc = np.zeros((H, W, 3), np.float32)
+    count = np.float32(0)
+    for p, s in enumerate((16, 8, 4, 2, 1)):
+        data, _ = port.render(world, W, H, s, 1, p)
+        port.accumulate(acc, data, s)
+        count = np.float32(count + np.float32(1.0) / np.float32(s * s))
+    assert np.array_equal(bits(frame), bits(port.resolve(acc, count)))
+
+
+# ------------------------------------------------------- bands / full sizes
+
+
+def test_row_bands_equal_full_frame(renderer, small_sky, builtin_objects):
+    """The multi-GPU partition rendered band by band on one
+    GPU equals the single launch bit for bit."""
+    from ray_tracing_b200.distributed import all_bands
+
+    renderer.upload_skybox(small_sky)
+    renderer.upload_scene(builtin_objects[0])
+    for W, H, s, world in ((320, 180, 1, 8), (320, 184, 4, 3)):
+        full, st = renderer.render_frame(Camera(), W, H, s)
+        parts = np.zeros_like(full)
+        rays = 0
+        for r0, r1 in all_bands(H, s, world):
+            if r1 > r0:
+                band, bst = renderer.render_frame(Camera(), W, H, s, rows=(r0, r1), band_only_fb=1)
+                parts[r0:r1] = band
+                rays += bst["rays"]
+        assert np.array_equal(bits(full), bits(parts))
+        assert rays == st["rays"]
+
+
+def test_4k_properties(renderer, port, real_sky, builtin_objects):
+    """BASELINE.json config 3 size (3840x2160): too large for the oracle to be
+    quick, so use size-independent properties -- determinism, kernel
+    equivalence, band invariance -- plus oracle parity on sampled bands."""
+    W, H = 3840, 2160
+    renderer.upload_skybox(real_sky)
+    renderer.upload_scene(builtin_objects[0])
+    a, sa = renderer.render_frame(Camera(), W, H, 1, kernel=RT_KERNEL_PERSISTENT)
+    b, sb = renderer.render_frame(Camera(), W, H, 1, kernel=RT_KERNEL_PIXEL)
+    assert np.array_equal(bits(a), bits(b)) and sa["rays"] == sb["rays"]
+    c, _ = renderer.render_frame(Camera(), W, H, 1, kernel=RT_KERNEL_PERSISTENT)
+    assert np.array_equal(bits(a), bits(c))
+    world = port.world(builtin_objects[0], real_sky)
+    for r0 in (0, 1000, 2100):
+        want = np.zeros((H, W, 3), np.float32)
+        port.render(world, W, H, 1, 1, 0, rows=(r0, r0 + 24), out=want)
+        assert np.array_equal(bits(a[r0:r0 + 24]), bits(want[r0:r0 + 24]))
+    assert a.min() >= 0.0 and a.max() <= 1.0
+
+
+# ------------------------------------------------------------------- LBVH
+
+
+def test_lbvh_equals_linear_scan_frames(renderer, small_sky):
+    objs = random_scene(1024, 77, spheres_only=True, extent=10.0)
+    renderer.upload_skybox(small_sky)
+    renderer.upload_scene(objs)
+    a, sa = renderer.render_frame(Camera(), 480, 270, 1, traversal=RT_TRAVERSAL_LINEAR)
+    b, sb = renderer.render_frame(Camera(), 480, 270, 1, traversal=RT_TRAVERSAL_LBVH)
+    assert np.array_equal(bits(a), bits(b)) and sa["rays"] == sb["rays"]
+
+
+def test_large_scene_lbvh_vs_oracle(renderer, port, small_sky):
+    """Config 5 in small: 20 000 spheres in the generator's layout (objects
+    beyond the shared-memory scan), far-away camera so D >> r stresses the
+    fuzzy sphere test; full frame at low resolution against the oracle."""
+    text = scenes.synthetic_spheres_text(20000, seed=20261017)
+    objs = host.parse_scene_string_large(text)
+    assert len(objs) == 20000
+    renderer.upload_skybox(small_sky)
+    renderer.upload_scene(objs)
+    world = port.world(objs, small_sky)
+    frame, st = renderer.render_frame(Camera(), 240, 136, 1)
+    want, rays = port.render(world, 240, 136, 1, 1, 0)
+    assert np.array_equal(bits(frame), bits(want))
+    assert st["rays"] == rays
+    far = Camera((120.0, 60.0, 140.0), (-1.0, -0.4, -1.1), (0, 1, 0), 30.0)
+    frame, st = renderer.render_frame(far, 160, 90, 1, pass_index=1)
+    want, rays = port.render(port.world(objs, small_sky, far.as_dict()), 160, 90, 1, 1, 1)
+    assert np.array_equal(bits(frame), bits(want))
+    assert st["rays"] == rays
