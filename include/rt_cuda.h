@@ -236,6 +236,9 @@ int rt_cuda_debug_camera_rays(const RtCamera *cam, const float *pxpy, int n, flo
 int rt_cuda_debug_rng(uint64_t state, int n, uint64_t *u64_out, float *f32_out);
 int rt_cuda_debug_random_directions(uint64_t state, int n, float *out3);
 uint64_t rt_pixel_key(float px, float py, uint64_t pass_index);
+/* Register-only FP32 issue-rate probe: TFLOP/s of FMA chains (fma=1) or of
+ * MUL+ADD pairs (fma=0, the ceiling of the no-contraction exact build). */
+int rt_cuda_debug_fp32_peak(int fma, float *tflops_out);
 
 #ifdef __cplusplus
 }

@@ -817,3 +817,60 @@ extern "C" int rt_cuda_debug_random_directions(uint64_t state, int n, float *out
 {
 	return rng_probe(state, n, nullptr, nullptr, out3);
 }
+
+/* ------------------------------------------------------ FP32 peak probe */
+
+/* Register-only FMA (or MUL+ADD) chains: the measured FP32 issue-rate ceiling
+ * the roofline fraction is quoted against.  8 independent
+ * chains per thread, 2 flops per FMA / per MUL+ADD pair. */
+template <bool FMA>
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float *out, int iters, float a, float b)
+{
+	float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.0f, x2 = x0 + 2.0f, x3 = x0 + 3.0f;
+	float x4 = x0 + 4.0f, x5 = x0 + 5.0f, x6 = x0 + 6.0f, x7 = x0 + 7.0f;
+	for (int i = 0; i < iters; i++) {
+#pragma unroll
+		for (int k = 0; k < 16; k++) {
+			if (FMA) {
+				x0 = __fmaf_rn(x0, a, b); x1 = __fmaf_rn(x1, a, b); x2 = __fmaf_rn(x2, a, b); x3 = __fmaf_rn(x3, a, b);
+				x4 = __fmaf_rn(x4, a, b); x5 = __fmaf_rn(x5, a, b); x6 = __fmaf_rn(x6, a, b); x7 = __fmaf_rn(x7, a, b);
+			} else {
+				x0 = __fadd_rn(__fmul_rn(x0, a), b); x1 = __fadd_rn(__fmul_rn(x1, a), b);
+				x2 = __fadd_rn(__fmul_rn(x2, a), b); x3 = __fadd_rn(__fmul_rn(x3, a), b);
+				x4 = __fadd_rn(__fmul_rn(x4, a), b); x5 = __fadd_rn(__fmul_rn(x5, a), b);
+				x6 = __fadd_rn(__fmul_rn(x6, a), b); x7 = __fadd_rn(__fmul_rn(x7, a), b);
+			}
+		}
+	}
+	float s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+	if (s == 12345.678f) out[0] = s;    /* keep the chains alive */
+}
+
+/* Returns measured TFLOP/s (2 flops per FMA, or per MUL+ADD pair when fma == 0). */
+extern "C" int rt_cuda_debug_fp32_peak(int fma, float *tflops_out)
+{
+	int rc = require_ready();
+	if (rc != RT_OK) return rc;
+	DeviceCtx &d = g.dev[0];
+	if ((rc = select_device(d)) != RT_OK) return rc;
+	TempBuf out;
+	CU(out.alloc(sizeof(float)));
+	const int iters = 2048, threads = 256;
+	int blocks = d.sm_count * 8;
+	float best = 0.0f;
+	for (int rep = 0; rep < 5; rep++) {
+		CU(cudaEventRecord(d.ev[0], d.stream));
+		if (fma) fp32_peak_kernel<true><<<blocks, threads, 0, d.stream>>>((float *) out.p, iters, 0.999f, 0.001f);
+		else     fp32_peak_kernel<false><<<blocks, threads, 0, d.stream>>>((float *) out.p, iters, 0.999f, 0.001f);
+		CU(cudaGetLastError());
+		CU(cudaEventRecord(d.ev[1], d.stream));
+		CU(cudaStreamSynchronize(d.stream));
+		float ms = 0.0f;
+		CU(cudaEventElapsedTime(&ms, d.ev[0], d.ev[1]));
+		double flops = 2.0 * 8.0 * 16.0 * (double) iters * (double) threads * (double) blocks;
+		float tf = (float) (flops / (ms * 1e-3) / 1e12);
+		if (rep > 0 && tf > best) best = tf;
+	}
+	*tflops_out = best;
+	return RT_OK;
+}

@@ -120,21 +120,41 @@ __device__ __forceinline__ void count_rays(const RtRenderParams &P, unsigned ray
 	if ((threadIdx.x & 31) == 0 && rays) atomicAdd(P.ray_counter, (unsigned long long) rays);
 }
 
-/* One trace + state transition for the lane's path. */
+/*
+ * One warp step: every lane with a pending ray traces it, then the warp walks
+ * classify -> draw loop -> launch together (see rt_device.cuh).  Must be called
+ * by all 32 lanes (it contains warp votes); lanes in MODE_IDLE just follow.
+ * Returns 1 for lanes that traced a ray.
+ */
 template <bool LBVH>
-__device__ __forceinline__ void path_step(Path &p, const RtRenderParams &P, const SharedScene &S)
+__device__ __forceinline__ unsigned warp_step(Path &p, const RtRenderParams &P, const SharedScene &S)
 {
-	f3 dn = unit3(p.ray_d);                 /* scene.c:158 */
-	RayQ q = ray_quadratic(dn);
-	Hit h;
-	if (LBVH) h = nearest_lbvh(P.bvh, P.scene.geomA, P.scene.geomB, p.ray_o, dn, q);
-	else      h = nearest_linear(S.A, S.B, P.scene.n, p.ray_o, dn, q);
-	f3 ro = p.ray_o;
-	path_advance(p, h, dn, P.scene, P.sky, S.lut,
-	             [&](const Hit &hh, f3 d, f3 &point, f3 &normal) {
-		             if (LBVH) surface_of(hh, __ldg(&P.scene.geomA[hh.obj]), __ldg(&P.scene.geomB[hh.obj]), ro, d, point, normal);
-		             else      surface_of(hh, S.A[hh.obj], S.B[hh.obj], ro, d, point, normal);
-	             });
+	const unsigned full = 0xffffffffu;
+	unsigned traced = 0;
+	if (p.mode == MODE_TRACE) {
+		f3 ro = p.ray_o;
+		f3 dn = unit3(p.ray_d);             /* scene.c:158 */
+		RayQ q = ray_quadratic(dn);
+		Hit h;
+		if (LBVH) h = nearest_lbvh(P.bvh, P.scene.geomA, P.scene.geomB, ro, dn, q);
+		else      h = nearest_linear(S.A, S.B, P.scene.n, ro, dn, q);
+		traced = 1;
+		path_classify(p, h, dn, P.scene, P.sky, S.lut,
+		              [&](const Hit &hh, f3 d, f3 &point, f3 &normal) {
+			              if (LBVH) surface_of(hh, __ldg(&P.scene.geomA[hh.obj]), __ldg(&P.scene.geomB[hh.obj]), ro, d, point, normal);
+			              else      surface_of(hh, S.A[hh.obj], S.B[hh.obj], ro, d, point, normal);
+		              });
+	}
+	f3 v = mk(0.0f, 0.0f, 0.0f);
+	bool renorm = false, launch = false;
+	while (__any_sync(full, p.mode == MODE_SAMPLING || p.mode == MODE_SHADE)) {
+		if (p.mode == MODE_SAMPLING || p.mode == MODE_SHADE) {
+			path_draw(p, P.scene.mat, v, renorm);
+			launch = launch || p.mode == MODE_TRACE;
+		}
+	}
+	if (launch) path_launch(p, v, renorm);
+	return traced;
 }
 
 /* ---------------------------------------------------------------- kernels */
@@ -146,19 +166,21 @@ render_pixel_kernel(const __grid_constant__ RtRenderParams P)
 	extern __shared__ __align__(16) unsigned char smem[];
 	SharedScene S = stage_scene(P, smem, !LBVH);
 
+	const unsigned full = 0xffffffffu;
 	unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
 	unsigned rays = 0;
 	int cx, cy;
-	if (idx < (unsigned) (P.tiles_x * P.tiles_y) * 32u && cell_of(P, idx, cx, cy)) {
-		Cell c = cell_geometry(P, cx, cy);
-		Path p;
+	Path p;
+	p.mode = MODE_IDLE;
+	Cell c;
+	bool owns = idx < (unsigned) (P.tiles_x * P.tiles_y) * 32u && cell_of(P, idx, cx, cy);
+	if (owns) {
+		c = cell_geometry(P, cx, cy);
 		path_begin(p, P.cam, c.u, c.v, P.pass_mix);
-		while (p.alive) {
-			path_step<LBVH>(p, P, S);
-			rays++;
-		}
-		store_cell(P, c, path_final(p));
 	}
+	while (__any_sync(full, p.mode != MODE_IDLE))
+		rays += warp_step<LBVH>(p, P, S);
+	if (owns) store_cell(P, c, path_final(p));
 	count_rays(P, rays);
 }
 
@@ -176,7 +198,7 @@ render_persistent_kernel(const __grid_constant__ RtRenderParams P)
 	const unsigned total = (unsigned) (P.tiles_x * P.tiles_y) * 32u;
 
 	Path p;
-	p.alive = false;
+	p.mode = MODE_IDLE;
 	Cell c;
 	bool owns = false;          /* lane holds a pixel whose path is running or just ended */
 	unsigned rays = 0;
@@ -184,9 +206,9 @@ render_persistent_kernel(const __grid_constant__ RtRenderParams P)
 	bool exhausted = false;                   /* warp-uniform */
 
 	for (;;) {
-		unsigned idle = __ballot_sync(full, !p.alive);
+		unsigned idle = __ballot_sync(full, p.mode == MODE_IDLE);
 		if (idle) {
-			if (!p.alive && owns) {
+			if (p.mode == MODE_IDLE && owns) {
 				store_cell(P, c, path_final(p));
 				owns = false;
 			}
@@ -201,21 +223,18 @@ render_persistent_kernel(const __grid_constant__ RtRenderParams P)
 			unsigned avail = batch_end - batch_next;
 			unsigned rank = __popc(idle & ((1u << lane) - 1u));
 			int cx, cy;
-			if (!p.alive && rank < avail && cell_of(P, batch_next + rank, cx, cy)) {
+			if (p.mode == MODE_IDLE && rank < avail && cell_of(P, batch_next + rank, cx, cy)) {
 				c = cell_geometry(P, cx, cy);
 				path_begin(p, P.cam, c.u, c.v, P.pass_mix);
 				owns = true;
 			}
 			batch_next += min((unsigned) __popc(idle), avail);
 		}
-		if (__ballot_sync(full, p.alive) == 0) {
+		if (__ballot_sync(full, p.mode != MODE_IDLE) == 0) {
 			if (exhausted && batch_next == batch_end) break;
 			continue;       /* only clipped cells were handed out; fetch more */
 		}
-		if (p.alive) {
-			path_step<LBVH>(p, P, S);
-			rays++;
-		}
+		rays += warp_step<LBVH>(p, P, S);
 	}
 	count_rays(P, rays);
 }

@@ -135,6 +135,7 @@ EXPORTED_SYMBOLS = [
     "rt_cuda_debug_rng",
     "rt_cuda_debug_random_directions",
     "rt_pixel_key",
+    "rt_cuda_debug_fp32_peak",
 ]
 
 _lib = None
@@ -186,6 +187,7 @@ def load_library() -> C.CDLL:
     L.rt_cuda_debug_camera_rays.argtypes = [C.POINTER(RtCamera), C.c_void_p, C.c_int, C.c_float, C.c_void_p]
     L.rt_cuda_debug_rng.argtypes = [C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
     L.rt_cuda_debug_random_directions.argtypes = [C.c_uint64, C.c_int, C.c_void_p]
+    L.rt_cuda_debug_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_float)]
     L.rt_pixel_key.restype = C.c_uint64
     L.rt_pixel_key.argtypes = [C.c_float, C.c_float, C.c_uint64]
     _lib = L
@@ -470,6 +472,11 @@ class Renderer:
         f = np.zeros(n, np.float32)
         _check(self.lib.rt_cuda_debug_rng(state, n, u.ctypes.data, f.ctypes.data))
         return u, f
+
+    def fp32_peak_tflops(self, fma: bool = True) -> float:
+        out = C.c_float()
+        _check(self.lib.rt_cuda_debug_fp32_peak(1 if fma else 0, C.byref(out)))
+        return out.value
 
     def debug_random_directions(self, state: int, n: int):
         out = np.zeros((n, 3), np.float32)
