@@ -239,6 +239,10 @@ uint64_t rt_pixel_key(float px, float py, uint64_t pass_index);
 /* Register-only FP32 issue-rate probe: TFLOP/s of FMA chains (fma=1) or of
  * MUL+ADD pairs (fma=0, the ceiling of the no-contraction exact build). */
 int rt_cuda_debug_fp32_peak(int fma, float *tflops_out);
+/* Bit-compare the render kernels' hoisted-reciprocal division with IEEE `/` on
+ * blocks*256*per_thread operand pairs (exponent ranges given); see rt_device.cuh. */
+int rt_cuda_debug_div_check(uint64_t seed, unsigned blocks, unsigned per_thread, int lo_exp_b, int hi_exp_b,
+                            int lo_exp_a, int hi_exp_a, uint64_t *mismatches);
 
 #ifdef __cplusplus
 }

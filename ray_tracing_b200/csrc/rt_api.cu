@@ -33,7 +33,9 @@
 	                                             float *, cudaStream_t);                                 \
 	extern "C" cudaError_t ns##_launch_probe_camera(const RtCameraFrame *, const float *, int, float *,  \
 	                                                cudaStream_t);                                       \
-	extern "C" cudaError_t ns##_launch_probe_rng(uint64_t, int, uint64_t *, float *, float *, cudaStream_t);
+	extern "C" cudaError_t ns##_launch_probe_rng(uint64_t, int, uint64_t *, float *, float *, cudaStream_t);      \
+	extern "C" cudaError_t ns##_launch_probe_div(uint64_t, unsigned, unsigned, int, int, int, int,             \
+	                                             unsigned long long *, cudaStream_t);
 DECLARE_VARIANT(rt_exact)
 DECLARE_VARIANT(rt_fast)
 
@@ -92,6 +94,7 @@ struct Context {
 	int       n = 0, light_index = -1;
 	RtVector3 light_pos = {0, 0, 0};
 	bool      have_scene = false, have_bvh = false;
+	int       div_safe = 0;
 	int       sky_w = 0, sky_h = 0;
 	bool      have_sky = false;
 	RtScene  *scene_cache = nullptr;    /* copy of the last RtScene given to render_frame_cuda */
@@ -247,6 +250,7 @@ extern "C" int rt_cuda_upload_objects(const RtObject *objects, int n)
 	g.n = n;
 	g.light_index = ps.light_index;
 	g.light_pos = ps.light_pos;
+	g.div_safe = ps.div_safe;
 	g.have_scene = true;
 	g.have_bvh = want_bvh;
 	rt_host_free_packed(&ps);
@@ -339,6 +343,7 @@ static void fill_views(const DeviceCtx &d, RtRenderParams &P)
 	P.scene.n = g.n;
 	P.scene.light_index = g.light_index;
 	P.scene.light_pos = g.light_pos;
+	P.scene.div_safe = g.div_safe;
 	P.bvh = rt_lbvh_view(&d.bvh);
 	P.sky.texels = d.sky;
 	P.sky.w = g.sky_w;
@@ -872,5 +877,26 @@ extern "C" int rt_cuda_debug_fp32_peak(int fma, float *tflops_out)
 		if (rep > 0 && tf > best) best = tf;
 	}
 	*tflops_out = best;
+	return RT_OK;
+}
+
+/* Bit-compare the hoisted division (rt_device.cuh: div_hoisted) with the IEEE
+ * `/` on blocks*256*per_thread pseudo-random operand pairs whose exponents lie
+ * in [lo_b, hi_b] (divisor) and [lo_a, hi_a] (dividend). */
+extern "C" int rt_cuda_debug_div_check(uint64_t seed, unsigned blocks, unsigned per_thread, int lo_b, int hi_b,
+                                       int lo_a, int hi_a, uint64_t *mismatches)
+{
+	int rc = require_ready();
+	if (rc != RT_OK) return rc;
+	DeviceCtx &d = g.dev[0];
+	if ((rc = select_device(d)) != RT_OK) return rc;
+	TempBuf cnt;
+	CU(cnt.alloc(sizeof(unsigned long long)));
+	CU(cudaMemsetAsync(cnt.p, 0, sizeof(unsigned long long), d.stream));
+	CU(rt_exact_launch_probe_div(seed, blocks, per_thread, lo_b, hi_b, lo_a, hi_a, (unsigned long long *) cnt.p, d.stream));
+	unsigned long long h = 0;
+	CU(cudaMemcpyAsync(&h, cnt.p, sizeof(h), cudaMemcpyDeviceToHost, d.stream));
+	CU(cudaStreamSynchronize(d.stream));
+	*mismatches = h;
 	return RT_OK;
 }

@@ -49,6 +49,7 @@ typedef struct {
 	/* bounds of all primitives (used for LBVH padding) */
 	RtVector3 bounds_lo, bounds_hi;
 	int       num_spheres, num_cubes;
+	int       div_safe;      /* every cube coordinate is zero or has magnitude in [2^-37, 2^59] */
 } RtPackedScene;
 
 int  rt_host_pack_scene(const RtObject *objects, int n, RtPackedScene *out);

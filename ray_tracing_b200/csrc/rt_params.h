@@ -22,6 +22,7 @@ struct RtSceneView {
 	int           n;
 	int           light_index;
 	RtVector3     light_pos;
+	int           div_safe;   /* every box coordinate is zero or in [2^-37, 2^59] (rt_device.cuh: ray_div) */
 };
 
 struct RtSkyView {

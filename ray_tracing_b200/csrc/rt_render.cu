@@ -121,15 +121,13 @@ __device__ __forceinline__ void count_rays(const RtRenderParams &P, unsigned ray
 }
 
 /*
- * One warp step: every lane with a pending ray traces it, then the warp walks
- * classify -> draw loop -> launch together (see rt_device.cuh).  Must be called
- * by all 32 lanes (it contains warp votes); lanes in MODE_IDLE just follow.
- * Returns 1 for lanes that traced a ray.
+ * One warp step: every lane with a pending ray traces it and consumes the hit
+ * (classify), then every lane that still has a surface to work on builds its
+ * next ray (launch).  Returns 1 for lanes that traced a ray.
  */
 template <bool LBVH>
 __device__ __forceinline__ unsigned warp_step(Path &p, const RtRenderParams &P, const SharedScene &S)
 {
-	const unsigned full = 0xffffffffu;
 	unsigned traced = 0;
 	if (p.mode == MODE_TRACE) {
 		f3 ro = p.ray_o;
@@ -137,7 +135,7 @@ __device__ __forceinline__ unsigned warp_step(Path &p, const RtRenderParams &P, 
 		RayQ q = ray_quadratic(dn);
 		Hit h;
 		if (LBVH) h = nearest_lbvh(P.bvh, P.scene.geomA, P.scene.geomB, ro, dn, q);
-		else      h = nearest_linear(S.A, S.B, P.scene.n, ro, dn, q);
+		else      h = nearest_linear(S.A, S.B, P.scene.n, ro, dn, q, P.scene.div_safe);
 		traced = 1;
 		path_classify(p, h, dn, P.scene, P.sky, S.lut,
 		              [&](const Hit &hh, f3 d, f3 &point, f3 &normal) {
@@ -145,15 +143,7 @@ __device__ __forceinline__ unsigned warp_step(Path &p, const RtRenderParams &P, 
 			              else      surface_of(hh, S.A[hh.obj], S.B[hh.obj], ro, d, point, normal);
 		              });
 	}
-	f3 v = mk(0.0f, 0.0f, 0.0f);
-	bool renorm = false, launch = false;
-	while (__any_sync(full, p.mode == MODE_SAMPLING || p.mode == MODE_SHADE)) {
-		if (p.mode == MODE_SAMPLING || p.mode == MODE_SHADE) {
-			path_draw(p, P.scene.mat, v, renorm);
-			launch = launch || p.mode == MODE_TRACE;
-		}
-	}
-	if (launch) path_launch(p, v, renorm);
+	if (p.mode == MODE_LAUNCH) path_launch(p, P.scene);
 	return traced;
 }
 
@@ -253,7 +243,7 @@ __global__ void probe_trace_kernel(RtRenderParams P, const float *rays6, int n, 
 	RayQ q = ray_quadratic(d);
 	Hit h;
 	if (LBVH) h = nearest_lbvh(P.bvh, P.scene.geomA, P.scene.geomB, o, d, q);
-	else      h = nearest_linear(S.A, S.B, P.scene.n, o, d, q);
+	else      h = nearest_linear(S.A, S.B, P.scene.n, o, d, q, P.scene.div_safe);
 	float *r = out7 + 7 * (size_t) i;
 	obj[i] = h.obj;
 	if (h.obj < 0) {                        /* scene.c:175-181 */
@@ -301,6 +291,33 @@ __global__ void probe_rng_kernel(uint64_t state, int n, uint64_t *u64_out, float
 		f3 d = random_direction(s);
 		dir_out[3 * i] = d.x; dir_out[3 * i + 1] = d.y; dir_out[3 * i + 2] = d.z;
 	}
+}
+
+/* div_hoisted(a, b, recip_refine(b)) against nvcc's IEEE a / b on pseudo-random
+ * operand pairs inside the guarded range; counts bit mismatches. */
+__global__ void probe_div_kernel(uint64_t seed, unsigned per_thread, int lo_exp_b, int hi_exp_b, int lo_exp_a,
+                                 int hi_exp_a, unsigned long long *mismatches)
+{
+	uint64_t st = splitmix64(seed ^ ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) * 0x9e3779b97f4a7c15ull);
+	unsigned bad = 0;
+	for (unsigned i = 0; i < per_thread; i++) {
+		uint64_t r1 = wyhash64(st), r2 = wyhash64(st);
+		unsigned eb = (unsigned) (lo_exp_b + 127) + (unsigned) ((r1 >> 40) % (unsigned) (hi_exp_b - lo_exp_b + 1));
+		unsigned ea = (unsigned) (lo_exp_a + 127) + (unsigned) ((r2 >> 40) % (unsigned) (hi_exp_a - lo_exp_a + 1));
+		unsigned mb = (unsigned) r1 & 0x7fffffu, ma = (unsigned) r2 & 0x7fffffu;
+		/* bias some mantissas towards the hard cases: all ones / all zeros / few bits */
+		unsigned sel = (unsigned) (r1 >> 60);
+		if (sel == 0) mb = 0x7fffffu; else if (sel == 1) mb = 0; else if (sel == 2) mb &= 0x7f0000u;
+		sel = (unsigned) (r2 >> 60);
+		if (sel == 0) ma = 0x7fffffu; else if (sel == 1) ma = 0; else if (sel == 2) ma &= 0x7f0000u;
+		float b = __uint_as_float(((unsigned) (r1 >> 63) << 31) | (eb << 23) | mb);
+		float a = __uint_as_float(((unsigned) (r2 >> 63) << 31) | (ea << 23) | ma);
+		if (i % 97 == 0) a = (r2 & 1) ? 0.0f : -0.0f;
+		float want = a / b;
+		float got = div_hoisted(a, b, recip_refine(b));
+		bad += __float_as_uint(want) != __float_as_uint(got);
+	}
+	if (bad) atomicAdd(mismatches, (unsigned long long) bad);
 }
 
 } // namespace RT_NS
@@ -397,6 +414,13 @@ extern "C" cudaError_t RT_FN(launch_probe_camera)(const RtCameraFrame *cam, cons
 {
 	if (n <= 0) return cudaSuccess;
 	RT_NS::probe_camera_kernel<<<(n + 127) / 128, 128, 0, stream>>>(*cam, pxpy, n, rays6);
+	return cudaGetLastError();
+}
+
+extern "C" cudaError_t RT_FN(launch_probe_div)(uint64_t seed, unsigned blocks, unsigned per_thread, int lo_b, int hi_b,
+                                                int lo_a, int hi_a, unsigned long long *mismatches, cudaStream_t stream)
+{
+	RT_NS::probe_div_kernel<<<blocks, 256, 0, stream>>>(seed, per_thread, lo_b, hi_b, lo_a, hi_a, mismatches);
 	return cudaGetLastError();
 }
 

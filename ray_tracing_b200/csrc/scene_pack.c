@@ -34,6 +34,13 @@ void rt_host_byte_lut(float lut[256])
 		lut[i] = (float) (uint8_t) i / 255;     /* gpu_and_windowing.c:107-109 */
 }
 
+/* guard of the hoisted slab-test division (rt_device.cuh: ray_div) */
+static int coord_safe(float x)
+{
+	float a = x < 0 ? -x : x;
+	return x == 0 || (a >= 0x1p-37f && a <= 0x1p59f);
+}
+
 static void grow(RtVector3 *lo, RtVector3 *hi, float x, float y, float z)
 {
 	if (x < lo->x) lo->x = x;
@@ -49,6 +56,7 @@ int rt_host_pack_scene(const RtObject *objects, int n, RtPackedScene *out)
 	memset(out, 0, sizeof(*out));
 	out->n = n;
 	out->light_index = -1;
+	out->div_safe = 1;
 	size_t cnt = n > 0 ? (size_t) n : 1;
 	out->geomA = (RtF4 *) calloc(cnt, sizeof(RtF4));
 	out->geomB = (RtF4 *) calloc(cnt, sizeof(RtF4));
@@ -86,6 +94,9 @@ int rt_host_pack_scene(const RtObject *objects, int n, RtPackedScene *out)
 			B->w = int_as_float(o->type == RT_OBJECT_CUBE ? RT_OBJECT_CUBE : 2);
 			grow(&out->bounds_lo, &out->bounds_hi, A->x, A->y, A->z);
 			grow(&out->bounds_lo, &out->bounds_hi, B->x, B->y, B->z);
+			if (!(coord_safe(A->x) && coord_safe(A->y) && coord_safe(A->z) &&
+			      coord_safe(B->x) && coord_safe(B->y) && coord_safe(B->z)))
+				out->div_safe = 0;
 			out->num_cubes++;
 		}
 

@@ -136,6 +136,7 @@ EXPORTED_SYMBOLS = [
     "rt_cuda_debug_random_directions",
     "rt_pixel_key",
     "rt_cuda_debug_fp32_peak",
+    "rt_cuda_debug_div_check",
 ]
 
 _lib = None
@@ -188,6 +189,7 @@ def load_library() -> C.CDLL:
     L.rt_cuda_debug_rng.argtypes = [C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
     L.rt_cuda_debug_random_directions.argtypes = [C.c_uint64, C.c_int, C.c_void_p]
     L.rt_cuda_debug_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_float)]
+    L.rt_cuda_debug_div_check.argtypes = [C.c_uint64, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
     L.rt_pixel_key.restype = C.c_uint64
     L.rt_pixel_key.argtypes = [C.c_float, C.c_float, C.c_uint64]
     _lib = L
@@ -472,6 +474,11 @@ class Renderer:
         f = np.zeros(n, np.float32)
         _check(self.lib.rt_cuda_debug_rng(state, n, u.ctypes.data, f.ctypes.data))
         return u, f
+
+    def div_check(self, seed: int, blocks: int, per_thread: int, lo_b=-40, hi_b=40, lo_a=-60, hi_a=60) -> int:
+        bad = C.c_uint64()
+        _check(self.lib.rt_cuda_debug_div_check(seed, blocks, per_thread, lo_b, hi_b, lo_a, hi_a, C.byref(bad)))
+        return bad.value
 
     def fp32_peak_tflops(self, fma: bool = True) -> float:
         out = C.c_float()

@@ -107,6 +107,18 @@ def test_trace_random_scenes_linear_and_lbvh(renderer, port, seed, n, spheres):
         assert np.array_equal(bits(hit), bits(want_hit))
 
 
+def test_hoisted_division_is_ieee(renderer):
+    """The slab test divides by a per-ray refined reciprocal (rt_device.cuh:
+    div_hoisted); inside the guarded operand range it must equal IEEE a / b bit
+    for bit.  ~1.2e9 operand pairs incl. all-ones / all-zeros mantissas, +-0."""
+    assert renderer.div_check(1, 148 * 8, 1024) == 0                       # the guarded range
+    assert renderer.div_check(2, 148 * 8, 1024, -40, -38, 58, 60) == 0     # largest quotients
+    assert renderer.div_check(3, 148 * 8, 1024, 38, 40, -60, -58) == 0     # smallest quotients
+    assert renderer.div_check(4, 148 * 8, 1024, -1, 1, -10, 10) == 0       # typical magnitudes
+    # outside the guard the sequence is NOT exact (that is why the guard exists)
+    assert renderer.div_check(5, 148, 256, 10, 20, -126, -120) > 0         # denormal quotients
+
+
 # ------------------------------------------------------------------ frames
 
 GOLD_CASES = [
