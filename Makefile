@@ -10,7 +10,7 @@ SRC       := ray_tracing_b200/csrc
 OBJ       := build/obj
 LIB       := ray_tracing_b200/libraytrace_b200.so
 NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Iinclude -I$(SRC) -Xcompiler -fPIC -Xcompiler -ffp-contract=off \
-             --expt-relaxed-constexpr -Xptxas -v
+             --expt-relaxed-constexpr -Xptxas -v $(NVFLAGS_EXTRA)
 # host C: the reference's own flags matter for float parity (no contraction)
 CFLAGS    := -std=c11 -O2 -fPIC -ffp-contract=off -Wall -Wextra -Iinclude -I$(SRC)
 

@@ -176,8 +176,12 @@ render_pixel_kernel(const __grid_constant__ RtRenderParams P)
 
 #define RT_WARP_BATCH 8     /* tiles (of 32 pixels) a warp claims per global atomic */
 
+#ifndef RT_PERSISTENT_MIN_BLOCKS
+#define RT_PERSISTENT_MIN_BLOCKS 8   /* 64 registers: 32 warps/SM; measured 3.36 -> 3.21 ms on 4K scene_0 */
+#endif
+
 template <bool LBVH>
-__global__ void __launch_bounds__(RT_BLOCK_THREADS)
+__global__ void __launch_bounds__(RT_BLOCK_THREADS, RT_PERSISTENT_MIN_BLOCKS)
 render_persistent_kernel(const __grid_constant__ RtRenderParams P)
 {
 	extern __shared__ __align__(16) unsigned char smem[];
