@@ -242,9 +242,27 @@ def main_gpu(args):
     band = torch.empty((max(r1 - r0, 1), W, 3), dtype=torch.float32, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
     common = dict(scale=1, pass_index=0, rows=(r0, r1), band_only_fb=1, variant=variant, kernel=kernel)
+    p2p = world > 1 and args.composite == "p2p"
+    shared_ptr = None
+    if p2p:
+        # fused composite: every rank's render kernel stores its band straight into
+        # rank 0's frame through a peer mapping (cudaIpc), no gather collective
+        box = [None]
+        if rank == 0:
+            shared_ptr, handle = r.shared_frame_create(W * H * 12)
+            box[0] = handle
+        dist.broadcast_object_list(box, src=0)
+        if rank != 0:
+            shared_ptr = r.shared_frame_open(box[0])
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        p2p_opts = dict(scale=1, pass_index=0, rows=(r0, r1), band_only_fb=0, variant=variant, kernel=kernel)
 
     def step_device():
-        # render this rank's band on torch's stream, then composite on rank 0
+        if p2p:
+            r.render_into(cam, shared_ptr, W, H, stream=stream, **p2p_opts)
+            dist.all_reduce(flag)      # stream-ordered completion signal: rank 0's frame is whole after it
+            return None
+        # render this rank's band on torch's stream, then gather on rank 0 (NCCL)
         r.render_into(cam, band.data_ptr(), W, H, stream=stream, **common)
         if world > 1:
             return gather_bands(band, H, W, 1, rank, world, dist, dst=0)
@@ -305,8 +323,11 @@ def main_gpu(args):
         else:
             full = step_device()
             if rank == 0:
-                host_frame.copy_(full, non_blocking=True)
-                torch.cuda.current_stream().synchronize()
+                if p2p:
+                    r.copy_to_host(host_frame.data_ptr(), shared_ptr, W * H * 12, stream)
+                else:
+                    host_frame.copy_(full, non_blocking=True)
+                    torch.cuda.current_stream().synchronize()
 
     for _ in range(3):
         step_e2e()
@@ -351,6 +372,7 @@ def main_gpu(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
                 "workload": WORKLOAD, "variant": args.variant, "kernel": args.kernel, "skybox": sky_desc,
+                "composite": ("none (1 GPU)" if world == 1 else ("fused P2P: band kernels store into rank 0's frame over NVLink (cudaIpc mapping) + 4-byte all_reduce as completion signal" if p2p else "NCCL gather of bands to rank 0")),
                 "framebuffer": "Vector3 f32x3 (reference frame format), bottom row first",
                 "l2": "no explicit flush: every step reads the 96 MiB RGBA8 skybox at random and writes a 99.5 MB frame (working set 196 MB > 126 MB L2)",
                 "rays_per_step": rays_per_step, "pixels_per_step": W * H,
@@ -361,7 +383,7 @@ def main_gpu(args):
                 "h2d_bytes_per_step": 4096,            # RtRenderParams kernel-argument block (camera frame, views, sizes)
                 "d2h_bytes_per_step": W * H * 12,
                 "frames_per_s": e2e_steps / e2e_s, "steps": e2e_steps,
-                "api": "render_frame_cuda_ex(cam, host Vector3 frame, w, h, opts) [N>1: band render + NCCL gather + D2H on rank 0]",
+                "api": "render_frame_cuda_ex(cam, host Vector3 frame, w, h, opts) [N>1: band render + composite on GPU 0 + D2H on rank 0]",
             },
             "gpu_launches": args.steps * world,        # one render kernel per rank per step (NCCL kernels not counted)
             "clocks": clocks,
@@ -386,9 +408,17 @@ def main_gpu(args):
             except Exception as e:
                 line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "unavailable", "sample": f"{type(e).__name__}: {e}"}
         print(json.dumps(line))
-    r.close()
     if world > 1:
         dist.barrier()
+    if p2p:
+        torch.cuda.synchronize()
+        if rank != 0:
+            r.shared_frame_close(shared_ptr, owner=False)
+        dist.barrier()
+        if rank == 0:
+            r.shared_frame_close(shared_ptr, owner=True)
+    r.close()
+    if world > 1:
         dist.destroy_process_group()
     return 0
 
@@ -402,6 +432,7 @@ def main():
     ap.add_argument("--variant", default="exact", choices=["exact", "fast"])
     ap.add_argument("--kernel", default="auto", choices=["auto", "pixel", "persistent"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--composite", default="p2p", choices=["p2p", "nccl"], help="N>1: how bands reach rank 0")
     args = ap.parse_args()
     if args.impl == "reference":
         return main_reference(args)

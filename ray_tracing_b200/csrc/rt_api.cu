@@ -900,3 +900,66 @@ extern "C" int rt_cuda_debug_div_check(uint64_t seed, unsigned blocks, unsigned 
 	*mismatches = h;
 	return RT_OK;
 }
+
+/* ------------------------------------------- cross-process frame sharing */
+
+/*
+ * One-process-per-GPU composite without a collective: rank 0 allocates the
+ * frame with rt_cuda_shared_frame_create() and hands the 64-byte handle to the
+ * other ranks (any transport; bench.py uses torch.distributed); they map it
+ * with rt_cuda_shared_frame_open() and pass the mapped address as `fb` with
+ * their row band, so the render kernel's epilogue stores the band straight
+ * into GPU 0's memory over NVLink (peer stores; SURVEY.md 8(e) option (a)).
+ */
+extern "C" int rt_cuda_shared_frame_create(size_t bytes, void **dev_ptr, void *handle64)
+{
+	int rc = require_ready();
+	if (rc != RT_OK) return rc;
+	if (!dev_ptr || !handle64 || bytes == 0) return fail(RT_ERR_ARG, "bad shared frame request");
+	if ((rc = select_device(g.dev[0])) != RT_OK) return rc;
+	void *p = nullptr;
+	CU(cudaMalloc(&p, bytes));
+	cudaIpcMemHandle_t h;
+	cudaError_t e = cudaIpcGetMemHandle(&h, p);
+	if (e != cudaSuccess) {
+		cudaFree(p);
+		return fail(RT_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+	}
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+	memcpy(handle64, &h, 64);
+	*dev_ptr = p;
+	return RT_OK;
+}
+
+extern "C" int rt_cuda_shared_frame_open(const void *handle64, void **dev_ptr)
+{
+	int rc = require_ready();
+	if (rc != RT_OK) return rc;
+	if (!dev_ptr || !handle64) return fail(RT_ERR_ARG, "bad shared frame handle");
+	if ((rc = select_device(g.dev[0])) != RT_OK) return rc;
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle64, 64);
+	void *p = nullptr;
+	CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+	*dev_ptr = p;
+	return RT_OK;
+}
+
+extern "C" int rt_cuda_shared_frame_close(void *dev_ptr, int owner)
+{
+	if (!dev_ptr) return RT_OK;
+	if (owner) CU(cudaFree(dev_ptr));
+	else CU(cudaIpcCloseMemHandle(dev_ptr));
+	return RT_OK;
+}
+
+/* Plain device->host copy of a library-owned frame (rank 0's read-back). */
+extern "C" int rt_cuda_copy_to_host(void *host_dst, const void *dev_src, size_t bytes, void *stream)
+{
+	int rc = require_ready();
+	if (rc != RT_OK) return rc;
+	cudaStream_t st = stream ? (cudaStream_t) stream : g.dev[0].stream;
+	CU(cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	return RT_OK;
+}

@@ -137,6 +137,10 @@ EXPORTED_SYMBOLS = [
     "rt_pixel_key",
     "rt_cuda_debug_fp32_peak",
     "rt_cuda_debug_div_check",
+    "rt_cuda_shared_frame_create",
+    "rt_cuda_shared_frame_open",
+    "rt_cuda_shared_frame_close",
+    "rt_cuda_copy_to_host",
 ]
 
 _lib = None
@@ -190,6 +194,10 @@ def load_library() -> C.CDLL:
     L.rt_cuda_debug_random_directions.argtypes = [C.c_uint64, C.c_int, C.c_void_p]
     L.rt_cuda_debug_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_float)]
     L.rt_cuda_debug_div_check.argtypes = [C.c_uint64, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+    L.rt_cuda_shared_frame_create.argtypes = [C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]
+    L.rt_cuda_shared_frame_open.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.rt_cuda_shared_frame_close.argtypes = [C.c_void_p, C.c_int]
+    L.rt_cuda_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.rt_pixel_key.restype = C.c_uint64
     L.rt_pixel_key.argtypes = [C.c_float, C.c_float, C.c_uint64]
     _lib = L
@@ -438,6 +446,25 @@ class Renderer:
         cam = camera.as_struct()
         _check(self.lib.rt_cuda_render_sweep(C.byref(cam), C.c_void_p(dst), w, h, init_scale, first_pass, C.byref(o), C.byref(st) if stats else None))
         return out, _stats_dict(st)
+
+    # -- cross-process frame on GPU 0 (fused P2P composite)
+    def shared_frame_create(self, nbytes: int):
+        ptr = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        _check(self.lib.rt_cuda_shared_frame_create(nbytes, C.byref(ptr), handle))
+        return ptr.value, bytes(handle)
+
+    def shared_frame_open(self, handle: bytes) -> int:
+        ptr = C.c_void_p()
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+        _check(self.lib.rt_cuda_shared_frame_open(buf, C.byref(ptr)))
+        return ptr.value
+
+    def shared_frame_close(self, ptr: int, owner: bool) -> None:
+        _check(self.lib.rt_cuda_shared_frame_close(C.c_void_p(ptr), 1 if owner else 0))
+
+    def copy_to_host(self, host_ptr: int, dev_ptr: int, nbytes: int, stream=None) -> None:
+        _check(self.lib.rt_cuda_copy_to_host(C.c_void_p(host_ptr), C.c_void_p(dev_ptr), nbytes, C.c_void_p(stream) if stream else None))
 
     def accum_reset(self) -> None:
         _check(self.lib.rt_cuda_accum_reset())
