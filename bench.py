@@ -255,7 +255,8 @@ def main_gpu(args):
         if rank != 0:
             shared_ptr = r.shared_frame_open(box[0])
         flag = torch.zeros(1, dtype=torch.int32, device=dev)
-        p2p_opts = dict(scale=1, pass_index=0, rows=(r0, r1), band_only_fb=0, variant=variant, kernel=kernel)
+        # rows are dealt to ranks in blocks of 16, round robin (sky rows and scene rows cost very different amounts)
+        p2p_opts = dict(scale=1, pass_index=0, interleave_count=world, interleave_index=rank, variant=variant, kernel=kernel)
 
     def step_device():
         if p2p:
@@ -274,7 +275,10 @@ def main_gpu(args):
         torch.cuda.synchronize()
 
     # rays of one step (exact count from the kernels; identical every step: pass 0)
-    st = r.render_into(cam, band.data_ptr(), W, H, stats=True, **common)
+    if p2p:
+        st = r.render_into(cam, shared_ptr, W, H, stats=True, **p2p_opts)
+    else:
+        st = r.render_into(cam, band.data_ptr(), W, H, stats=True, **common)
     rays_t = torch.tensor([st["rays"]], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(rays_t)
@@ -304,7 +308,10 @@ def main_gpu(args):
     torch.cuda.synchronize()
     k0.record()
     for _ in range(args.steps):
-        r.render_into(cam, band.data_ptr(), W, H, stream=stream, **common)
+        if p2p:
+            r.render_into(cam, shared_ptr, W, H, stream=stream, **p2p_opts)
+        else:
+            r.render_into(cam, band.data_ptr(), W, H, stream=stream, **common)
     k1.record()
     torch.cuda.synchronize()
     kern_ms = torch.tensor([k0.elapsed_time(k1) / args.steps], dtype=torch.float64, device=dev)
@@ -357,7 +364,7 @@ def main_gpu(args):
         peak = muladd_peak if variant == host.RT_VARIANT_EXACT else fma_peak
         kern_rays = st["rays"]                       # this rank's band
         achieved = kern_rays * FLOPS_PER_RAY[SCENE] / (kern_ms * 1e-3) / 1e12
-        band_px = (r1 - r0) * W
+        band_px = (W * H) // world
         algo_bytes = band_px * 12 + band_px * 32     # Vector3 store + one 32 B skybox sector per escaping path
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         traffic = None

@@ -189,6 +189,8 @@ typedef struct {
 	int      kernel;        /* RT_KERNEL_* */
 	int      band_only_fb;  /* 1: fb holds only the band's rows (row_begin maps to fb row 0) */
 	void    *stream;        /* cudaStream_t to launch on in one-device mode; NULL = library stream */
+	int      interleave_count; /* one-GPU-per-process ranks sharing a frame: this call renders the row   */
+	int      interleave_index; /* blocks (16 output rows) b of the band with b % count == index; 0/1 = all */
 } RtRenderOpts;
 
 typedef struct {

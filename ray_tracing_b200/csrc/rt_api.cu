@@ -399,37 +399,32 @@ extern "C" int rt_cuda_accum_reset(void)
 
 extern "C" float rt_cuda_accum_count(void) { return g.accum_count; }
 
-/* fb[p] = accum[p] * inv_count (main.c:467-477) over whole rows; used when a pass
- * leaves pixels uncovered (rows >= (h/scale)*scale, columns >= T*(w/T)): their
- * data counts as 0, but the frame is still accum / count everywhere. */
-__global__ void resolve_rows_kernel(const float *accum, size_t accum_first, void *fb, size_t fb_first,
-                                    int fmt, size_t count, float inv)
-{
-	size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
-	if (i >= count) return;
-	const float *a = accum + 3 * (accum_first + i);
-	float r = a[0] * inv, gch = a[1] * inv, b = a[2] * inv;
-	size_t p = fb_first + i;
-	if (fmt == RT_FB_F32X3) {
-		float *f = reinterpret_cast<float *>(fb) + 3 * p;
-		f[0] = r; f[1] = gch; f[2] = b;
-	} else {
-		reinterpret_cast<uchar4 *>(fb)[p] = make_uchar4((unsigned char) __float2uint_rz(r * 255.0f),
-		                                                (unsigned char) __float2uint_rz(gch * 255.0f),
-		                                                (unsigned char) __float2uint_rz(b * 255.0f), 255);
-	}
-}
-
 struct PassPlan {
 	int  w, h, scale, ncols;
 	int  row0, row1;          /* output band of the whole call */
 	bool lbvh, persistent, exact;
 };
 
+/* Rows of a band are dealt to GPUs (or ranks) in blocks of RT_INTERLEAVE_ROWS
+ * output rows, round robin: sky-heavy and scene-heavy rows cost very different
+ * amounts (1 vs up to 40 rays per pixel), so contiguous bands of H/N rows leave
+ * most GPUs idle.  The block size is fixed in OUTPUT rows so that a GPU owns the
+ * same pixels at every scale of a progressive sweep (its accumulation buffer
+ * stays valid across passes). */
+#define RT_INTERLEAVE_ROWS 16
+
+static int interleave_shift(int scale)
+{
+	int rows = (scale >= 1 && scale <= RT_INTERLEAVE_ROWS && RT_INTERLEAVE_ROWS % scale == 0) ? RT_INTERLEAVE_ROWS / scale : 4;
+	int sh = 0;
+	while ((1 << sh) < rows) sh++;
+	return sh;       /* low-res rows per block = 1 << shift */
+}
+
 /* Launch one pass for one device over output rows [r0, r1) (scale aligned). */
 static int launch_band(DeviceCtx &d, const RtCamera *cam, const PassPlan &pl, const RtRenderOpts *o,
-                       void *fb, int fb_row_offset, int r0, int r1, cudaStream_t stream, bool accumulate,
-                       float accum_weight, float inv_count, int *launches)
+                       void *fb, int fb_row_offset, int r0, int r1, int il_n, int il_i, cudaStream_t stream,
+                       bool accumulate, float accum_weight, float inv_count, int *launches)
 {
 	RtRenderParams P;
 	memset(&P, 0, sizeof(P));
@@ -445,8 +440,18 @@ static int launch_band(DeviceCtx &d, const RtCamera *cam, const PassPlan &pl, co
 	P.lrow0 = r0 / pl.scale;
 	P.lrow1 = std::min((r1 + pl.scale - 1) / pl.scale, P.lh);
 	if (P.lrow1 < P.lrow0) P.lrow1 = P.lrow0;
+	P.il_n = il_n > 1 ? il_n : 1;
+	P.il_i = il_n > 1 ? il_i : 0;
+	P.il_shift = interleave_shift(pl.scale);
+	{
+		/* low-res rows of [lrow0, lrow1) owned by this GPU: blocks b with b % il_n == il_i */
+		int per = 1 << P.il_shift, total = P.lrow1 - P.lrow0, mine = 0;
+		for (int b = P.il_i, start = P.il_i * per; start < total; b += P.il_n, start += P.il_n * per)
+			mine += std::min(per, total - start);
+		P.local_rows = mine;
+	}
 	P.tiles_x = (P.cells_per_row + RT_TILE_W - 1) / RT_TILE_W;
-	P.tiles_y = (P.lrow1 - P.lrow0 + RT_TILE_H - 1) / RT_TILE_H;
+	P.tiles_y = (P.local_rows + RT_TILE_H - 1) / RT_TILE_H;
 	P.pass_mix = rt_host_splitmix64(o->pass_index);
 	P.fb = fb;
 	P.fb_format = o->fb_format;
@@ -457,12 +462,13 @@ static int launch_band(DeviceCtx &d, const RtCamera *cam, const PassPlan &pl, co
 	P.inv_count = inv_count;
 
 	/* Pixels the reference's pass never writes (main.c:285-290: rows >=
-	 * lh*scale; main.c:363: columns >= T*column_w): a fresh frame holds 0 there,
-	 * an accumulated frame keeps accum/count. */
+	 * lh*scale; main.c:363: columns >= T*column_w) hold 0: a fresh frame is
+	 * zeroed there, and an accumulated frame never receives data there, so its
+	 * accum/count is 0 too.  One GPU (interleave index 0) clears them. */
 	int covered_rows_end = std::min(P.lh * pl.scale, r1);
 	bool uncovered = covered_rows_end < r1 || P.column_w * pl.ncols < pl.w;
 	size_t bpp = bytes_per_pixel(o->fb_format);
-	if (uncovered && !accumulate) {
+	if (uncovered && P.il_i == 0) {
 		int s0 = P.column_w * pl.ncols < pl.w ? r0 : std::max(covered_rows_end, r0);
 		CU(cudaMemsetAsync((char *) fb + (size_t) (s0 - fb_row_offset) * pl.w * bpp, 0,
 		                   (size_t) (r1 - s0) * pl.w * bpp, stream));
@@ -484,14 +490,6 @@ static int launch_band(DeviceCtx &d, const RtCamera *cam, const PassPlan &pl, co
 		(*launches)++;
 	}
 
-	if (uncovered && accumulate) {
-		size_t count = (size_t) (r1 - r0) * pl.w;
-		resolve_rows_kernel<<<(unsigned) ((count + 255) / 256), 256, 0, stream>>>(
-		    d.accum, (size_t) (r0 - d.accum_row0) * pl.w, fb, (size_t) (r0 - fb_row_offset) * pl.w,
-		    o->fb_format, count, inv_count);
-		CU(cudaGetLastError());
-		(*launches)++;
-	}
 	return RT_OK;
 }
 
@@ -548,20 +546,22 @@ static int render_pass(const RtCamera *cam, void *fb, int w, int h, const RtRend
 	bool use_user_stream = ngpu == 1 && o->stream != nullptr;
 	int launches = 0;
 
-	/* contiguous row bands, aligned to scale */
-	int band_r0[RT_MAX_GPUS], band_r1[RT_MAX_GPUS];
-	int lrows = (band_rows + pl.scale - 1) / pl.scale;
-	int start_l = 0;
+	/* Several GPUs in this process: every GPU gets the whole call band and renders
+	 * the row blocks it owns (round robin), storing straight into GPU 0's frame. */
+	int il_n = 1, il_base = 0;
+	if (o->interleave_count > 1) {
+		if (o->interleave_index < 0 || o->interleave_index >= o->interleave_count)
+			return fail(RT_ERR_ARG, "interleave_index out of range");
+		if (ngpu > 1) return fail(RT_ERR_ARG, "interleave_count is for one-GPU-per-process ranks; this context already spans %d GPUs", ngpu);
+		il_n = o->interleave_count;
+		il_base = o->interleave_index;
+	} else if (ngpu > 1)
+		il_n = ngpu;
 	bool fresh_accum = false;
 	for (int i = 0; i < ngpu; i++) {
-		int take = lrows / ngpu + (i < lrows % ngpu ? 1 : 0);
-		band_r0[i] = pl.row0 + start_l * pl.scale;
-		band_r1[i] = std::min(pl.row0 + (start_l + take) * pl.scale, pl.row1);
-		start_l += take;
 		DeviceCtx &d = g.dev[i];
 		if ((rc = select_device(d)) != RT_OK) return rc;
-		if (accumulate && band_r1[i] > band_r0[i] &&
-		    (rc = ensure_accum(d, w, h, band_r0[i], band_r1[i] - band_r0[i], &fresh_accum)) != RT_OK) return rc;
+		if (accumulate && (rc = ensure_accum(d, w, h, pl.row0, band_rows, &fresh_accum)) != RT_OK) return rc;
 		if (pl.lbvh) {
 			/* the LBVH padding covers ray origins up to d_max away (rt_lbvh.cu) */
 			float need = rt_lbvh_required_dmax(&d.bvh, cam->pos);
@@ -584,17 +584,15 @@ static int render_pass(const RtCamera *cam, void *fb, int w, int h, const RtRend
 
 	for (int i = 0; i < ngpu; i++) {
 		DeviceCtx &d = g.dev[i];
-		int r0 = band_r0[i], r1 = band_r1[i];
 		if ((rc = select_device(d)) != RT_OK) return rc;
 		cudaStream_t st = use_user_stream ? (cudaStream_t) o->stream : d.stream;
 		if (stats) {
 			CU(cudaMemsetAsync(d.ray_counter, 0, sizeof(unsigned long long), st));
 			CU(cudaEventRecord(d.ev[0], st));
 		}
-		if (r1 > r0) {
-			rc = launch_band(d, cam, pl, o, target, fb_row_offset, r0, r1, st, accumulate, wgt, inv, &launches);
-			if (rc != RT_OK) return rc;
-		}
+		rc = launch_band(d, cam, pl, o, target, fb_row_offset, pl.row0, pl.row1, il_n, ngpu > 1 ? i : il_base, st,
+		                 accumulate, wgt, inv, &launches);
+		if (rc != RT_OK) return rc;
 		if (stats) CU(cudaEventRecord(d.ev[1], st));
 	}
 

@@ -61,7 +61,9 @@ struct RtRenderParams {
 	int cells_per_col;        /* ceil(column_w / scale): visible low-res pixels per column row */
 	int cells_per_row;        /* num_columns * cells_per_col */
 	int lrow0, lrow1;         /* low-res row band [lrow0, lrow1) rendered by this launch */
-	int tiles_x, tiles_y;     /* 8x4 tiles covering cells_per_row x (lrow1-lrow0) */
+	int il_n, il_i, il_shift; /* this launch owns row blocks b (of 1<<il_shift low-res rows) with b % il_n == il_i */
+	int local_rows;           /* low-res rows of the band owned by this launch */
+	int tiles_x, tiles_y;     /* 8x4 tiles covering cells_per_row x local_rows */
 	uint64_t pass_mix;        /* splitmix64(pass_index) */
 
 	/* output */

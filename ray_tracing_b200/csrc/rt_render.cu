@@ -52,8 +52,11 @@ __device__ __forceinline__ bool cell_of(const RtRenderParams &P, unsigned idx, i
 	unsigned tile = idx >> 5, lane = idx & 31;
 	int tx = (int) (tile % (unsigned) P.tiles_x), ty = (int) (tile / (unsigned) P.tiles_x);
 	cx = tx * RT_TILE_W + (int) (lane & (RT_TILE_W - 1));
-	cy = ty * RT_TILE_H + (int) (lane / RT_TILE_W);
-	return cx < P.cells_per_row && cy < (P.lrow1 - P.lrow0);
+	int ly = ty * RT_TILE_H + (int) (lane / RT_TILE_W);     /* row among the rows this launch owns */
+	/* owned rows -> band rows: blocks of 1 << il_shift rows dealt round robin */
+	int blk = ly >> P.il_shift;
+	cy = ((blk * P.il_n + P.il_i) << P.il_shift) + (ly - (blk << P.il_shift));
+	return cx < P.cells_per_row && ly < P.local_rows && cy < (P.lrow1 - P.lrow0);
 }
 
 struct Cell {

@@ -14,7 +14,9 @@ from typing import Callable, List, Tuple
 
 def band_rows(h: int, scale: int, rank: int, world: int, row0: int = 0, row1: "int | None" = None) -> Tuple[int, int]:
     """Contiguous band [r0, r1) of output rows for `rank`, aligned to `scale`
-    (a low-res row is never split; main.c:290 iterates low-res rows)."""
+    (a low-res row is never split; main.c:290 iterates low-res rows).  For a
+    progressive sweep pass scale=16 (the coarsest scale) for every pass so each
+    rank keeps one accumulation band."""
     row1 = h if row1 is None else row1
     lrows = (row1 - row0 + scale - 1) // scale
     base, extra = divmod(lrows, world)

@@ -78,6 +78,8 @@ class RtRenderOpts(C.Structure):
         ("kernel", C.c_int),
         ("band_only_fb", C.c_int),
         ("stream", C.c_void_p),
+        ("interleave_count", C.c_int),
+        ("interleave_index", C.c_int),
     ]
 
 

@@ -327,6 +327,26 @@ def test_row_bands_equal_full_frame(renderer, small_sky, builtin_objects):
         assert rays == st["rays"]
 
 
+def test_interleaved_row_blocks_equal_full_frame(renderer, small_sky, builtin_objects):
+    """The multi-GPU work split: each rank renders the 16-row blocks b with
+    b % N == rank straight into one shared frame.  Done here by one GPU playing
+    every rank in turn; the union must equal the single launch, rays included."""
+    import torch
+
+    renderer.upload_skybox(small_sky)
+    renderer.upload_scene(builtin_objects[0])
+    for W, H, s, world in ((320, 200, 1, 3), (320, 200, 4, 8), (130, 70, 16, 2), (96, 54, 3, 2)):
+        full, st = renderer.render_frame(Camera(), W, H, s)
+        frame = torch.full((H, W, 3), -1.0, dtype=torch.float32, device="cuda")
+        rays = 0
+        for rank in range(world):
+            bst = renderer.render_into(Camera(), frame.data_ptr(), W, H, stats=True, scale=s,
+                                       interleave_count=world, interleave_index=rank)
+            rays += bst["rays"]
+        assert np.array_equal(bits(frame.cpu().numpy()), bits(full)), (W, H, s, world)
+        assert rays == st["rays"]
+
+
 def test_4k_properties(renderer, port, real_sky, builtin_objects):
     """BASELINE.json config 3 size (3840x2160): too large for the oracle to be
     quick, so use size-independent properties -- determinism, kernel
