@@ -256,7 +256,7 @@ def main_gpu(args):
             shared_ptr = r.shared_frame_open(box[0])
         flag = torch.zeros(1, dtype=torch.int32, device=dev)
         # rows are dealt to ranks in blocks of 16, round robin (sky rows and scene rows cost very different amounts)
-        p2p_opts = dict(scale=1, pass_index=0, interleave_count=world, interleave_index=rank, variant=variant, kernel=kernel)
+        p2p_opts = dict(scale=1, pass_index=0, interleave_count=world, interleave_index=rank, remote_fb=int(rank != 0), variant=variant, kernel=kernel)
 
     def step_device():
         if p2p:
@@ -379,7 +379,7 @@ def main_gpu(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
                 "workload": WORKLOAD, "variant": args.variant, "kernel": args.kernel, "skybox": sky_desc,
-                "composite": ("none (1 GPU)" if world == 1 else ("fused P2P: band kernels store into rank 0's frame over NVLink (cudaIpc mapping) + 4-byte all_reduce as completion signal" if p2p else "NCCL gather of bands to rank 0")),
+                "composite": ("none (1 GPU)" if world == 1 else ("P2P: ranks render their 16-row blocks (round robin) locally, then one strided peer copy per rank into rank 0's frame over NVLink (cudaIpc mapping) + 4-byte all_reduce as completion signal" if p2p else "NCCL gather of bands to rank 0")),
                 "framebuffer": "Vector3 f32x3 (reference frame format), bottom row first",
                 "l2": "no explicit flush: every step reads the 96 MiB RGBA8 skybox at random and writes a 99.5 MB frame (working set 196 MB > 126 MB L2)",
                 "rays_per_step": rays_per_step, "pixels_per_step": W * H,

@@ -421,6 +421,38 @@ static int interleave_shift(int scale)
 	return sh;       /* low-res rows per block = 1 << shift */
 }
 
+/* Copy the row blocks this GPU owns (interleave il_i of il_n) from its local
+ * frame to the same rows of `dst` (GPU 0's frame, peer memory) with the copy
+ * engine.  The render kernel stores 4-byte words pixel by pixel as paths end;
+ * done straight over NVLink those small scattered writes ran at ~12 GB/s per
+ * GPU (8-GPU 4K frame: 1.09 ms kernel vs 0.40 ms on local memory), so remote
+ * GPUs render locally and ship their blocks as one strided 2D copy. */
+static int copy_owned_blocks(void *dst, const void *src, const PassPlan &pl, int fb_row_offset, int il_n, int il_i,
+                             size_t bpp, cudaStream_t stream)
+{
+	int rows_per_block = (1 << interleave_shift(pl.scale)) * pl.scale;
+	int band = pl.row1 - pl.row0;
+	size_t row_bytes = (size_t) pl.w * bpp;
+	size_t chunk = (size_t) rows_per_block * row_bytes;
+	int nblocks = (band + rows_per_block - 1) / rows_per_block;
+	int last = nblocks - 1;
+	int last_rows = band - last * rows_per_block;
+	int mine = il_i < nblocks ? (nblocks - 1 - il_i) / il_n + 1 : 0;          /* blocks il_i, il_i + il_n, ... */
+	if (mine <= 0) return RT_OK;
+	bool own_partial_last = last_rows != rows_per_block && last % il_n == il_i;
+	int full = own_partial_last ? mine - 1 : mine;
+	size_t base = (size_t) (pl.row0 - fb_row_offset) * row_bytes + (size_t) il_i * chunk;
+	if (full > 0)
+		CU(cudaMemcpy2DAsync((char *) dst + base, (size_t) il_n * chunk, (const char *) src + base, (size_t) il_n * chunk,
+		                     chunk, (size_t) full, cudaMemcpyDeviceToDevice, stream));
+	if (own_partial_last) {
+		size_t off = (size_t) (pl.row0 - fb_row_offset) * row_bytes + (size_t) last * chunk;
+		CU(cudaMemcpyAsync((char *) dst + off, (const char *) src + off, (size_t) last_rows * row_bytes,
+		                   cudaMemcpyDeviceToDevice, stream));
+	}
+	return RT_OK;
+}
+
 /* Launch one pass for one device over output rows [r0, r1) (scale aligned). */
 static int launch_band(DeviceCtx &d, const RtCamera *cam, const PassPlan &pl, const RtRenderOpts *o,
                        void *fb, int fb_row_offset, int r0, int r1, int il_n, int il_i, cudaStream_t stream,
@@ -590,9 +622,25 @@ static int render_pass(const RtCamera *cam, void *fb, int w, int h, const RtRend
 			CU(cudaMemsetAsync(d.ray_counter, 0, sizeof(unsigned long long), st));
 			CU(cudaEventRecord(d.ev[0], st));
 		}
-		rc = launch_band(d, cam, pl, o, target, fb_row_offset, pl.row0, pl.row1, il_n, ngpu > 1 ? i : il_base, st,
+		/* a GPU whose destination frame lives on another GPU renders into its own
+		 * memory and ships the blocks it owns afterwards (copy_owned_blocks) */
+		bool remote = (ngpu > 1 && i > 0) || (o->interleave_count > 1 && o->remote_fb);
+		void *render_to = target;
+		if (remote) {
+			size_t need = fb_rows * (size_t) w * bpp;
+			if (d.fb_bytes < need) {
+				CU(cudaFree(d.fb));
+				d.fb = nullptr; d.fb_bytes = 0;
+				CU(cudaMalloc(&d.fb, need));
+				d.fb_bytes = need;
+			}
+			render_to = d.fb;
+		}
+		int il_i = ngpu > 1 ? i : il_base;
+		rc = launch_band(d, cam, pl, o, render_to, fb_row_offset, pl.row0, pl.row1, il_n, il_i, st,
 		                 accumulate, wgt, inv, &launches);
 		if (rc != RT_OK) return rc;
+		if (remote && (rc = copy_owned_blocks(target, render_to, pl, fb_row_offset, il_n, il_i, bpp, st)) != RT_OK) return rc;
 		if (stats) CU(cudaEventRecord(d.ev[1], st));
 	}
 

@@ -94,7 +94,7 @@ def _rank_main(rank, world, port_no, W, H, scale, tmp):
     dist.broadcast_object_list(box, src=0)
     if rank != 0:
         ptr = r.shared_frame_open(box[0])
-    r.render_into(cam, ptr, W, H, scale=scale, interleave_count=world, interleave_index=rank, stream=stream)
+    r.render_into(cam, ptr, W, H, scale=scale, interleave_count=world, interleave_index=rank, remote_fb=int(rank != 0), stream=stream)
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
     dist.all_reduce(flag)
     torch.cuda.synchronize()
