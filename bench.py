@@ -321,12 +321,15 @@ def main_gpu(args):
 
     # ---- end to end through the C ABI with a host framebuffer --------------
     # (rank 0 owns the host frame; with N>1 the bands are gathered to GPU 0 first)
-    host_frame = torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True) if rank == 0 else None
+    host_frames = [torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True) for _ in range(2)] if rank == 0 else None
+    host_frame = host_frames[0] if rank == 0 else None
+    e2e_opts = dict(scale=1, pass_index=0, variant=variant, kernel=kernel, stream=stream)
 
-    def step_e2e():
+    def step_e2e(i, pipeline):
         if world == 1:
-            # the drop-in call: params go H2D as kernel arguments, the Vector3 frame comes back D2H
-            r.render_into(cam, host_frame.data_ptr(), W, H, host=True, scale=1, pass_index=0, variant=variant, kernel=kernel, stream=stream)
+            # the drop-in call: params go H2D as kernel arguments, the Vector3 frame comes back D2H.
+            # pipeline=1: the call returns once the copy is queued; frame i+1 renders while frame i drains
+            r.render_into(cam, host_frames[i & 1].data_ptr(), W, H, host=True, pipeline=int(pipeline), **e2e_opts)
         else:
             full = step_device()
             if rank == 0:
@@ -336,18 +339,24 @@ def main_gpu(args):
                     host_frame.copy_(full, non_blocking=True)
                     torch.cuda.current_stream().synchronize()
 
-    for _ in range(3):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
+    def run_e2e(n, pipeline):
+        for i in range(3):
+            step_e2e(i, pipeline)
+        r.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(n):
+            step_e2e(i, pipeline)
+        r.synchronize()
+        barrier()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     e2e_steps = max(3, min(args.steps, 20))
-    for _ in range(e2e_steps):
-        step_e2e()
-    barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_s = float(e2e_s.item())
+    e2e_sync_s = run_e2e(e2e_steps, False)
+    e2e_s = run_e2e(e2e_steps, True) if world == 1 else e2e_sync_s
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
@@ -390,6 +399,8 @@ def main_gpu(args):
                 "h2d_bytes_per_step": 4096,            # RtRenderParams kernel-argument block (camera frame, views, sizes)
                 "d2h_bytes_per_step": W * H * 12,
                 "frames_per_s": e2e_steps / e2e_s, "steps": e2e_steps,
+                "mode": "pipelined: call k+1 renders while the copy stream drains frame k into the other pinned host frame; timed until rt_cuda_synchronize()" if world == 1 else "synchronous per step",
+                "sync_value": rays_per_step * e2e_steps / e2e_sync_s / 1e6,
                 "api": "render_frame_cuda_ex(cam, host Vector3 frame, w, h, opts) [N>1: band render + composite on GPU 0 + D2H on rank 0]",
             },
             "gpu_launches": args.steps * world,        # one render kernel per rank per step (NCCL kernels not counted)

@@ -191,6 +191,9 @@ typedef struct {
 	void    *stream;        /* cudaStream_t to launch on in one-device mode; NULL = library stream */
 	int      interleave_count; /* one-GPU-per-process ranks sharing a frame: this call renders the row   */
 	int      interleave_index; /* blocks (16 output rows) b of the band with b % count == index; 0/1 = all */
+	int      pipeline;         /* host `fb` only: return before the device->host copy has finished; frames of  */
+	                           /*    consecutive calls overlap (render k+1 || copy k).  `fb` should be pinned;    */
+	                           /*    it is valid after rt_cuda_synchronize()                                      */
 	int      remote_fb;        /* 1: `fb` is peer memory (another GPU's frame): render locally, then copy    */
 	                           /*    the owned blocks there with one strided device-to-device copy           */
 } RtRenderOpts;

@@ -84,6 +84,12 @@ struct DeviceCtx {
 	unsigned long long *ray_counter = nullptr;
 	unsigned int       *work_counter = nullptr;
 	unsigned long long *host_rays = nullptr;              /* pinned */
+	/* pipelined host read-back: two staging frames + a copy stream */
+	cudaStream_t copy_stream = nullptr;
+	void        *stage[2] = {nullptr, nullptr};
+	size_t       stage_bytes[2] = {0, 0};
+	cudaEvent_t  stage_rendered[2] = {nullptr, nullptr}, stage_copied[2] = {nullptr, nullptr};
+	int          stage_next = 0;
 };
 
 struct Context {
@@ -120,6 +126,12 @@ static void free_device(DeviceCtx &d)
 	cudaFree(d.ray_counter); cudaFree(d.work_counter);
 	if (d.host_rays) cudaFreeHost(d.host_rays);
 	for (auto &e : d.ev) if (e) cudaEventDestroy(e);
+	for (int k = 0; k < 2; k++) {
+		cudaFree(d.stage[k]);
+		if (d.stage_rendered[k]) cudaEventDestroy(d.stage_rendered[k]);
+		if (d.stage_copied[k]) cudaEventDestroy(d.stage_copied[k]);
+	}
+	if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
 	if (d.stream) cudaStreamDestroy(d.stream);
 	d = DeviceCtx();
 }
@@ -144,6 +156,11 @@ static int init_devices(const int *devices, int count)
 		CU(cudaSetDevice(d.device));
 		CU(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, d.device));
 		CU(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+		CU(cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking));
+		for (int k = 0; k < 2; k++) {
+			CU(cudaEventCreateWithFlags(&d.stage_rendered[k], cudaEventDisableTiming));
+			CU(cudaEventCreateWithFlags(&d.stage_copied[k], cudaEventDisableTiming));
+		}
 		for (auto &ev : d.ev) CU(cudaEventCreate(&ev));
 		CU(cudaMalloc(&d.ray_counter, sizeof(unsigned long long)));
 		CU(cudaMalloc(&d.work_counter, sizeof(unsigned int)));
@@ -204,6 +221,7 @@ extern "C" int rt_cuda_synchronize(void)
 	for (int i = 0; i < g.ngpu; i++) {
 		CU(cudaSetDevice(g.dev[i].device));
 		CU(cudaStreamSynchronize(g.dev[i].stream));
+		CU(cudaStreamSynchronize(g.dev[i].copy_stream));
 	}
 	CU(cudaSetDevice(g.dev[0].device));
 	return RT_OK;
@@ -511,9 +529,15 @@ static int launch_band(DeviceCtx &d, const RtCamera *cam, const PassPlan &pl, co
 		int grid = 0;
 		if (pl.persistent) {
 			CU(cudaMemsetAsync(d.work_counter, 0, sizeof(unsigned int), stream));
-			int per_sm = 0;
-			CU((pl.exact ? rt_exact_persistent_blocks_per_sm : rt_fast_persistent_blocks_per_sm)(&P, pl.lbvh, &per_sm));
-			if (per_sm < 1) per_sm = 1;
+			/* occupancy of the persistent kernel, queried once per (variant, traversal, scene size) */
+			static int cached_per_sm[2][2] = {{0, 0}, {0, 0}}, cached_n[2][2] = {{-1, -1}, {-1, -1}};
+			int &per_sm = cached_per_sm[pl.exact ? 0 : 1][pl.lbvh ? 1 : 0];
+			int &for_n = cached_n[pl.exact ? 0 : 1][pl.lbvh ? 1 : 0];
+			if (per_sm < 1 || for_n != P.scene.n) {
+				CU((pl.exact ? rt_exact_persistent_blocks_per_sm : rt_fast_persistent_blocks_per_sm)(&P, pl.lbvh, &per_sm));
+				if (per_sm < 1) per_sm = 1;
+				for_n = P.scene.n;
+			}
 			unsigned warps_needed = (unsigned) P.tiles_x * P.tiles_y;
 			unsigned blocks_needed = (warps_needed + (RT_BLOCK_THREADS / 32) - 1) / (RT_BLOCK_THREADS / 32);
 			grid = (int) std::min<unsigned>((unsigned) (d.sm_count * per_sm), blocks_needed);
@@ -562,6 +586,26 @@ static int render_pass(const RtCamera *cam, void *fb, int w, int h, const RtRend
 	bool dev_fb = o->fb_memory == RT_MEM_DEVICE || (o->fb_memory == RT_MEM_AUTO && is_device_pointer(fb));
 	DeviceCtx &d0 = g.dev[0];
 	void *target = fb;
+	/* Pipelined host read-back (opts->pipeline): the frame is rendered into one of
+	 * two staging buffers and copied to `fb` by the copy stream while the next
+	 * call already renders into the other one; the call returns without waiting.
+	 * `fb` is valid after rt_cuda_synchronize() (or once two later calls returned). */
+	bool pipelined = !dev_fb && o->pipeline && g.ngpu == 1 && !stats && o->interleave_count <= 1;
+	int slot = 0;
+	if (pipelined) {
+		size_t need = fb_rows * (size_t) w * bpp;
+		if ((rc = select_device(d0)) != RT_OK) return rc;
+		slot = d0.stage_next;
+		d0.stage_next ^= 1;
+		CU(cudaEventSynchronize(d0.stage_copied[slot]));       /* the copy that last used this slot */
+		if (d0.stage_bytes[slot] < need) {
+			CU(cudaFree(d0.stage[slot]));
+			d0.stage[slot] = nullptr; d0.stage_bytes[slot] = 0;
+			CU(cudaMalloc(&d0.stage[slot], need));
+			d0.stage_bytes[slot] = need;
+		}
+		target = d0.stage[slot];
+	} else
 	if (!dev_fb) {
 		size_t need = fb_rows * (size_t) w * bpp;
 		if ((rc = select_device(d0)) != RT_OK) return rc;
@@ -644,6 +688,14 @@ static int render_pass(const RtCamera *cam, void *fb, int w, int h, const RtRend
 		if (stats) CU(cudaEventRecord(d.ev[1], st));
 	}
 
+	if (pipelined) {
+		cudaStream_t st = use_user_stream ? (cudaStream_t) o->stream : d0.stream;
+		CU(cudaEventRecord(d0.stage_rendered[slot], st));
+		CU(cudaStreamWaitEvent(d0.copy_stream, d0.stage_rendered[slot], 0));
+		CU(cudaMemcpyAsync(fb, d0.stage[slot], fb_rows * (size_t) w * bpp, cudaMemcpyDeviceToHost, d0.copy_stream));
+		CU(cudaEventRecord(d0.stage_copied[slot], d0.copy_stream));
+		return RT_OK;
+	}
 	if (!sync_and_copy && !stats && dev_fb) {
 		cudaSetDevice(d0.device);
 		return RT_OK;       /* fully asynchronous call */

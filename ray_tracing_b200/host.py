@@ -80,6 +80,7 @@ class RtRenderOpts(C.Structure):
         ("stream", C.c_void_p),
         ("interleave_count", C.c_int),
         ("interleave_index", C.c_int),
+        ("pipeline", C.c_int),
         ("remote_fb", C.c_int),
     ]
 

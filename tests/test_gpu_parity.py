@@ -257,6 +257,23 @@ def test_u8x4_framebuffer(renderer, small_sky, builtin_objects):
     assert (u8[..., 3] == 255).all()
 
 
+def test_pipelined_host_readback(renderer, small_sky, builtin_objects):
+    """opts.pipeline: calls return before their device->host copy finished;
+    after rt_cuda_synchronize() every frame equals the synchronous call's."""
+    import torch
+
+    renderer.upload_skybox(small_sky)
+    renderer.upload_scene(builtin_objects[0])
+    W, H = 320, 180
+    want = [renderer.render_frame(Camera(), W, H, 1, pass_index=p)[0] for p in range(5)]
+    bufs = [torch.zeros((H, W, 3), dtype=torch.float32, pin_memory=True) for _ in range(5)]
+    for p in range(5):
+        renderer.render_into(Camera(), bufs[p].data_ptr(), W, H, host=True, pipeline=1, scale=1, pass_index=p)
+    renderer.synchronize()
+    for p in range(5):
+        assert np.array_equal(bits(bufs[p].numpy()), bits(want[p])), p
+
+
 # ------------------------------------------------- accumulate / sweep (R12)
 
 
