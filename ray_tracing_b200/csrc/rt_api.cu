@@ -105,6 +105,7 @@ struct Context {
 	bool      have_sky = false;
 	RtScene  *scene_cache = nullptr;    /* copy of the last RtScene given to render_frame_cuda */
 	float     accum_count = 0.0f;       /* accum_counts[] of main.c:89 (all columns advance together) */
+	float     sweep_tau2 = 4e-12f;      /* rt_device.cuh: sample_faces_surface; tests may override */
 };
 
 static Context g;
@@ -503,6 +504,9 @@ static int launch_band(DeviceCtx &d, const RtCamera *cam, const PassPlan &pl, co
 	P.tiles_x = (P.cells_per_row + RT_TILE_W - 1) / RT_TILE_W;
 	P.tiles_y = (P.local_rows + RT_TILE_H - 1) / RT_TILE_H;
 	P.pass_mix = rt_host_splitmix64(o->pass_index);
+	P.magic_tiles_x = ((1ull << 40) + (unsigned long long) std::max(P.tiles_x, 1) - 1) / (unsigned long long) std::max(P.tiles_x, 1);
+	P.magic_cells_per_col = ((1ull << 40) + (unsigned long long) std::max(P.cells_per_col, 1) - 1) / (unsigned long long) std::max(P.cells_per_col, 1);
+	P.sweep_tau2 = g.sweep_tau2;
 	P.fb = fb;
 	P.fb_format = o->fb_format;
 	P.fb_row_offset = fb_row_offset;
@@ -1059,5 +1063,16 @@ extern "C" int rt_cuda_copy_to_host(void *host_dst, const void *dev_src, size_t 
 	cudaStream_t st = stream ? (cudaStream_t) stream : g.dev[0].stream;
 	CU(cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
+	return RT_OK;
+}
+
+/* Test knob: threshold of the sign shortcut in the light-sample sweep
+ * (rt_device.cuh: sample_faces_surface).  A huge value forces the literal
+ * normalise-then-dot path for every sample; results must not change. */
+extern "C" int rt_cuda_debug_set_sweep_threshold(float tau2)
+{
+	float keep = g.sweep_tau2;
+	(void) keep;
+	g.sweep_tau2 = tau2 >= 0.0f ? tau2 : 4e-12f;
 	return RT_OK;
 }

@@ -65,6 +65,8 @@ struct RtRenderParams {
 	int local_rows;           /* low-res rows of the band owned by this launch */
 	int tiles_x, tiles_y;     /* 8x4 tiles covering cells_per_row x local_rows */
 	uint64_t pass_mix;        /* splitmix64(pass_index) */
+	unsigned long long magic_tiles_x, magic_cells_per_col;   /* ceil(2^40 / d): index math without integer division */
+	float    sweep_tau2;      /* rt_device.cuh: sample_faces_surface */
 
 	/* output */
 	void  *fb;                /* RT_FB_F32X3: float[3] per pixel; RT_FB_U8X4: uchar4 */

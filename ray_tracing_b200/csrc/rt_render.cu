@@ -28,13 +28,15 @@ struct SharedScene {
 	float4 *A;
 	float4 *B;
 	float  *lut;
+	unsigned char *sweep;     /* 32 bytes per warp: lane list of warp_sweep() */
 };
 
 __device__ __forceinline__ SharedScene stage_scene(const RtRenderParams &P, unsigned char *smem, bool linear)
 {
 	SharedScene s;
 	s.lut = reinterpret_cast<float *>(smem);
-	s.A = reinterpret_cast<float4 *>(smem + 256 * sizeof(float));
+	s.sweep = smem + 256 * sizeof(float) + 32 * (threadIdx.x >> 5);
+	s.A = reinterpret_cast<float4 *>(smem + 256 * sizeof(float) + RT_BLOCK_THREADS);
 	s.B = s.A + (linear ? P.scene.n : 0);
 	for (int i = threadIdx.x; i < 256; i += blockDim.x) s.lut[i] = __ldg(&P.byte_lut[i]);
 	if (linear)
@@ -46,11 +48,18 @@ __device__ __forceinline__ SharedScene stage_scene(const RtRenderParams &P, unsi
 	return s;
 }
 
+/* n / d for n*d < 2^40 with magic = ceil(2^40 / d) computed on the host */
+__device__ __forceinline__ unsigned div_magic(unsigned n, unsigned long long magic)
+{
+	return (unsigned) (((unsigned long long) n * magic) >> 40);
+}
+
 /* tile-ordered work index -> low-res cell (cx, cy) inside the band */
 __device__ __forceinline__ bool cell_of(const RtRenderParams &P, unsigned idx, int &cx, int &cy)
 {
 	unsigned tile = idx >> 5, lane = idx & 31;
-	int tx = (int) (tile % (unsigned) P.tiles_x), ty = (int) (tile / (unsigned) P.tiles_x);
+	unsigned tyu = div_magic(tile, P.magic_tiles_x);
+	int tx = (int) (tile - tyu * (unsigned) P.tiles_x), ty = (int) tyu;
 	cx = tx * RT_TILE_W + (int) (lane & (RT_TILE_W - 1));
 	int ly = ty * RT_TILE_H + (int) (lane / RT_TILE_W);     /* row among the rows this launch owns */
 	/* owned rows -> band rows: blocks of 1 << il_shift rows dealt round robin */
@@ -69,11 +78,14 @@ struct Cell {
 __device__ __forceinline__ Cell cell_geometry(const RtRenderParams &P, int cx, int cy)
 {
 	Cell c;
-	int col = cx / P.cells_per_col;
-	int i = cx - col * P.cells_per_col;
+	int col = 0, i = cx, column_x = 0, lcx = 0;
+	if (P.num_columns > 1) {            /* warp-uniform */
+		col = (int) div_magic((unsigned) cx, P.magic_cells_per_col);
+		i = cx - col * P.cells_per_col;
+		column_x = P.column_w * col;
+		lcx = column_x / P.scale;
+	}
 	int j = P.lrow0 + cy;
-	int column_x = P.column_w * col;
-	int lcx = column_x / P.scale;
 	float u = (float) (lcx + i) / (float) (P.lw - 1);
 	float v = (float) j / (float) (P.lh - 1);
 	c.u = 1.0f - u;
@@ -125,8 +137,10 @@ __device__ __forceinline__ void count_rays(const RtRenderParams &P, unsigned ray
 
 /*
  * One warp step: every lane with a pending ray traces it and consumes the hit
- * (classify), then every lane that still has a surface to work on builds its
- * next ray (launch).  Returns 1 for lanes that traced a ray.
+ * (classify), the warp shares out the light-sample tests of the new surfaces
+ * (sweep), then every lane that still has a surface to work on builds its next
+ * ray (launch).  Must be called by all 32 lanes.  Returns 1 for lanes that
+ * traced a ray.
  */
 template <bool LBVH>
 __device__ __forceinline__ unsigned warp_step(Path &p, const RtRenderParams &P, const SharedScene &S)
@@ -146,6 +160,7 @@ __device__ __forceinline__ unsigned warp_step(Path &p, const RtRenderParams &P, 
 			              else      surface_of(hh, S.A[hh.obj], S.B[hh.obj], ro, d, point, normal);
 		              });
 	}
+	warp_sweep(p, S.sweep, P.sweep_tau2);
 	if (p.mode == MODE_LAUNCH) path_launch(p, P.scene);
 	return traced;
 }
@@ -349,7 +364,7 @@ __global__ void probe_div_kernel(uint64_t seed, unsigned per_thread, int lo_exp_
 
 static size_t smem_bytes(const RtRenderParams &P, bool lbvh)
 {
-	return 256 * sizeof(float) + (lbvh ? 0 : 2 * sizeof(float4) * (size_t) P.scene.n);
+	return 256 * sizeof(float) + RT_BLOCK_THREADS + (lbvh ? 0 : 2 * sizeof(float4) * (size_t) P.scene.n);
 }
 
 template <class K>

@@ -141,6 +141,7 @@ EXPORTED_SYMBOLS = [
     "rt_pixel_key",
     "rt_cuda_debug_fp32_peak",
     "rt_cuda_debug_div_check",
+    "rt_cuda_debug_set_sweep_threshold",
     "rt_cuda_shared_frame_create",
     "rt_cuda_shared_frame_open",
     "rt_cuda_shared_frame_close",
@@ -202,6 +203,7 @@ def load_library() -> C.CDLL:
     L.rt_cuda_shared_frame_open.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     L.rt_cuda_shared_frame_close.argtypes = [C.c_void_p, C.c_int]
     L.rt_cuda_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.rt_cuda_debug_set_sweep_threshold.argtypes = [C.c_float]
     L.rt_pixel_key.restype = C.c_uint64
     L.rt_pixel_key.argtypes = [C.c_float, C.c_float, C.c_uint64]
     _lib = L
@@ -510,6 +512,9 @@ class Renderer:
         bad = C.c_uint64()
         _check(self.lib.rt_cuda_debug_div_check(seed, blocks, per_thread, lo_b, hi_b, lo_a, hi_a, C.byref(bad)))
         return bad.value
+
+    def set_sweep_threshold(self, tau2: float) -> None:
+        _check(self.lib.rt_cuda_debug_set_sweep_threshold(tau2))
 
     def fp32_peak_tflops(self, fma: bool = True) -> float:
         out = C.c_float()

@@ -257,6 +257,22 @@ def test_u8x4_framebuffer(renderer, small_sky, builtin_objects):
     assert (u8[..., 3] == 255).all()
 
 
+def test_sweep_sign_shortcut_equals_literal_path(renderer, small_sky, builtin_objects):
+    """The light-sample sweep decides rd.n > 0 from the un-normalised vector when
+    the sign is certain (rt_device.cuh: sample_faces_surface).  Forcing the
+    literal normalise-then-dot path for every sample must give the same frame."""
+    renderer.upload_skybox(small_sky)
+    for sc in (0, 1):
+        renderer.upload_scene(builtin_objects[sc])
+        a, sa = renderer.render_frame(Camera(), 640, 360, 1, pass_index=4)
+        renderer.set_sweep_threshold(1e30)
+        try:
+            b, sb = renderer.render_frame(Camera(), 640, 360, 1, pass_index=4)
+        finally:
+            renderer.set_sweep_threshold(-1.0)
+        assert np.array_equal(bits(a), bits(b)) and sa["rays"] == sb["rays"]
+
+
 def test_pipelined_host_readback(renderer, small_sky, builtin_objects):
     """opts.pipeline: calls return before their device->host copy finished;
     after rt_cuda_synchronize() every frame equals the synchronous call's."""
