@@ -73,6 +73,7 @@ struct DeviceCtx {
 	cudaEvent_t  ev[4] = {nullptr, nullptr, nullptr, nullptr};
 	/* scene */
 	float4 *geomA = nullptr, *geomB = nullptr, *mat = nullptr;
+	int2   *runs = nullptr;
 	RtLbvh  bvh;
 	/* skybox */
 	uchar4 *sky = nullptr;
@@ -100,7 +101,7 @@ struct Context {
 	int       n = 0, light_index = -1;
 	RtVector3 light_pos = {0, 0, 0};
 	bool      have_scene = false, have_bvh = false;
-	int       div_safe = 0;
+	int       div_safe = 0, num_runs = 0;
 	int       sky_w = 0, sky_h = 0;
 	bool      have_sky = false;
 	RtScene  *scene_cache = nullptr;    /* copy of the last RtScene given to render_frame_cuda */
@@ -120,7 +121,7 @@ static void free_device(DeviceCtx &d)
 {
 	if (d.device < 0) return;
 	cudaSetDevice(d.device);
-	cudaFree(d.geomA); cudaFree(d.geomB); cudaFree(d.mat);
+	cudaFree(d.geomA); cudaFree(d.geomB); cudaFree(d.mat); cudaFree(d.runs);
 	rt_lbvh_free(&d.bvh);
 	cudaFree(d.sky); cudaFree(d.lut);
 	cudaFree(d.fb); cudaFree(d.accum);
@@ -241,12 +242,26 @@ extern "C" int rt_cuda_upload_objects(const RtObject *objects, int n)
 
 	size_t cnt = n > 0 ? (size_t) n : 1;
 	bool want_bvh = n > RT_LBVH_THRESHOLD;
+	/* maximal runs of consecutive same-type objects, in scene order */
+	std::vector<int2> runs;
+	for (int i = 0; i < n;) {
+		int ty = (int) objects[i].type, j = i + 1;
+		while (j < n && (int) objects[j].type == ty && j - i < 0xffffff) j++;
+		runs.push_back(make_int2(i, (j - i) | ((ty & 0x7f) << 24)));
+		i = j;
+	}
 	for (int i = 0; i < g.ngpu; i++) {
 		DeviceCtx &d = g.dev[i];
 		if ((rc = select_device(d)) != RT_OK) { rt_host_free_packed(&ps); return rc; }
 		cudaStreamSynchronize(d.stream);
-		cudaFree(d.geomA); cudaFree(d.geomB); cudaFree(d.mat);
+		cudaFree(d.geomA); cudaFree(d.geomB); cudaFree(d.mat); cudaFree(d.runs);
 		d.geomA = d.geomB = d.mat = nullptr;
+		d.runs = nullptr;
+		if (cudaMalloc(&d.runs, sizeof(int2) * (runs.size() + 1)) != cudaSuccess ||
+		    (!runs.empty() && cudaMemcpy(d.runs, runs.data(), sizeof(int2) * runs.size(), cudaMemcpyHostToDevice) != cudaSuccess)) {
+			rt_host_free_packed(&ps);
+			return fail(RT_ERR_CUDA, "scene upload (runs): %s", cudaGetErrorString(cudaGetLastError()));
+		}
 		rt_lbvh_free(&d.bvh);
 		cudaError_t e;
 		if ((e = cudaMalloc(&d.geomA, cnt * sizeof(float4))) != cudaSuccess ||
@@ -270,6 +285,7 @@ extern "C" int rt_cuda_upload_objects(const RtObject *objects, int n)
 	g.light_index = ps.light_index;
 	g.light_pos = ps.light_pos;
 	g.div_safe = ps.div_safe;
+	g.num_runs = (int) runs.size();
 	g.have_scene = true;
 	g.have_bvh = want_bvh;
 	rt_host_free_packed(&ps);
@@ -363,6 +379,8 @@ static void fill_views(const DeviceCtx &d, RtRenderParams &P)
 	P.scene.light_index = g.light_index;
 	P.scene.light_pos = g.light_pos;
 	P.scene.div_safe = g.div_safe;
+	P.scene.runs = d.runs;
+	P.scene.num_runs = g.num_runs;
 	P.bvh = rt_lbvh_view(&d.bvh);
 	P.sky.texels = d.sky;
 	P.sky.w = g.sky_w;

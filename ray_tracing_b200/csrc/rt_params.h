@@ -22,6 +22,8 @@ struct RtSceneView {
 	int           n;
 	int           light_index;
 	RtVector3     light_pos;
+	const int2   *runs;       /* maximal runs of same-type objects: (first, count | type << 24) */
+	int           num_runs;
 	int           div_safe;   /* every box coordinate is zero or in [2^-37, 2^59] (rt_device.cuh: ray_div) */
 };
 

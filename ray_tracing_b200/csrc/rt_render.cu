@@ -29,6 +29,7 @@ struct SharedScene {
 	float4 *B;
 	float  *lut;
 	unsigned char *sweep;     /* 32 bytes per warp: lane list of warp_sweep() */
+	int2   *runs;             /* type runs of the scene (rt_device.cuh: nearest_linear) */
 };
 
 __device__ __forceinline__ SharedScene stage_scene(const RtRenderParams &P, unsigned char *smem, bool linear)
@@ -38,12 +39,15 @@ __device__ __forceinline__ SharedScene stage_scene(const RtRenderParams &P, unsi
 	s.sweep = smem + 256 * sizeof(float) + 32 * (threadIdx.x >> 5);
 	s.A = reinterpret_cast<float4 *>(smem + 256 * sizeof(float) + RT_BLOCK_THREADS);
 	s.B = s.A + (linear ? P.scene.n : 0);
+	s.runs = reinterpret_cast<int2 *>(s.B + (linear ? P.scene.n : 0));
 	for (int i = threadIdx.x; i < 256; i += blockDim.x) s.lut[i] = __ldg(&P.byte_lut[i]);
 	if (linear)
 		for (int i = threadIdx.x; i < P.scene.n; i += blockDim.x) {
 			s.A[i] = __ldg(&P.scene.geomA[i]);
 			s.B[i] = __ldg(&P.scene.geomB[i]);
 		}
+	if (linear)
+		for (int i = threadIdx.x; i < P.scene.num_runs; i += blockDim.x) s.runs[i] = P.scene.runs[i];
 	__syncthreads();
 	return s;
 }
@@ -152,7 +156,7 @@ __device__ __forceinline__ unsigned warp_step(Path &p, const RtRenderParams &P, 
 		RayQ q = ray_quadratic(dn);
 		Hit h;
 		if (LBVH) h = nearest_lbvh(P.bvh, P.scene.geomA, P.scene.geomB, ro, dn, q);
-		else      h = nearest_linear(S.A, S.B, P.scene.n, ro, dn, q, P.scene.div_safe);
+		else      h = nearest_linear(S.A, S.B, S.runs, P.scene.num_runs, P.scene.n, ro, dn, q, P.scene.div_safe);
 		traced = 1;
 		path_classify(p, h, dn, P.scene, P.sky, S.lut,
 		              [&](const Hit &hh, f3 d, f3 &point, f3 &normal) {
@@ -195,7 +199,7 @@ render_pixel_kernel(const __grid_constant__ RtRenderParams P)
 #define RT_WARP_BATCH 8     /* most tiles (of 32 pixels) a warp claims per global atomic */
 
 #ifndef RT_PERSISTENT_MIN_BLOCKS
-#define RT_PERSISTENT_MIN_BLOCKS 8   /* 64 registers: 32 warps/SM; measured 3.36 -> 3.21 ms on 4K scene_0 */
+#define RT_PERSISTENT_MIN_BLOCKS 6   /* 80 registers, 24 warps/SM: best of 5/6/8 on 4K scene_0 (2.39 / 2.37 / 2.51 ms) */
 #endif
 
 template <bool LBVH>
@@ -277,7 +281,7 @@ __global__ void probe_trace_kernel(RtRenderParams P, const float *rays6, int n, 
 	RayQ q = ray_quadratic(d);
 	Hit h;
 	if (LBVH) h = nearest_lbvh(P.bvh, P.scene.geomA, P.scene.geomB, o, d, q);
-	else      h = nearest_linear(S.A, S.B, P.scene.n, o, d, q, P.scene.div_safe);
+	else      h = nearest_linear(S.A, S.B, S.runs, P.scene.num_runs, P.scene.n, o, d, q, P.scene.div_safe);
 	float *r = out7 + 7 * (size_t) i;
 	obj[i] = h.obj;
 	if (h.obj < 0) {                        /* scene.c:175-181 */
@@ -364,7 +368,8 @@ __global__ void probe_div_kernel(uint64_t seed, unsigned per_thread, int lo_exp_
 
 static size_t smem_bytes(const RtRenderParams &P, bool lbvh)
 {
-	return 256 * sizeof(float) + RT_BLOCK_THREADS + (lbvh ? 0 : 2 * sizeof(float4) * (size_t) P.scene.n);
+	return 256 * sizeof(float) + RT_BLOCK_THREADS +
+	       (lbvh ? 0 : 2 * sizeof(float4) * (size_t) P.scene.n + sizeof(int2) * (size_t) P.scene.num_runs);
 }
 
 template <class K>
