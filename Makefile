@@ -9,6 +9,8 @@ ARCH      := -gencode arch=compute_100a,code=sm_100a
 SRC       := ray_tracing_b200/csrc
 OBJ       := build/obj
 LIB       := ray_tracing_b200/libraytrace_b200.so
+HARNESS   := tools/rt_headless
+STB_DIR   ?= /root/reference/3p
 NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Iinclude -I$(SRC) -Xcompiler -fPIC -Xcompiler -ffp-contract=off \
              --expt-relaxed-constexpr -Xptxas -v $(NVFLAGS_EXTRA)
 # host C: the reference's own flags matter for float parity (no contraction)
@@ -19,7 +21,7 @@ CUDA_OBJS := $(OBJ)/rt_api.o $(OBJ)/rt_lbvh.o $(OBJ)/rt_render_exact.o $(OBJ)/rt
 DEVICE_HDRS := $(SRC)/rt_device.cuh $(SRC)/rt_params.h $(SRC)/rt_host.h $(SRC)/rt_lbvh.h include/rt_cuda.h
 
 .PHONY: all oracle harness clean
-all: $(LIB)
+all: $(LIB) $(HARNESS)
 
 $(OBJ)/%.o: $(SRC)/%.c include/rt_cuda.h $(SRC)/rt_host.h
 	@mkdir -p $(OBJ)
@@ -46,6 +48,13 @@ $(LIB): $(HOST_OBJS) $(CUDA_OBJS)
 
 oracle:
 	$(MAKE) -C oracle all
+
+# headless C stand-in for the reference's main() on top of the C ABI.  stb_image
+# is used in place from the reference's vendored 3p/ when present (never copied).
+harness: $(HARNESS)
+$(HARNESS): tools/rt_headless.c include/rt_cuda.h $(LIB)
+	$(CC) -std=c11 -O2 -Iinclude $(if $(wildcard $(STB_DIR)/stb/stb_image.h),-DRT_HAVE_STB -I$(STB_DIR),) \
+	    -o $@ tools/rt_headless.c -Lray_tracing_b200 -lraytrace_b200 -Wl,-rpath,'$$ORIGIN/../ray_tracing_b200' -lm
 
 clean:
 	rm -rf build $(LIB)
