@@ -38,7 +38,10 @@ void rt_host_byte_lut(float lut[256])
 static int coord_safe(float x)
 {
 	float a = x < 0 ? -x : x;
-	return x == 0 || (a >= 0x1p-37f && a <= 0x1p59f);
+	uint32_t bits;
+	memcpy(&bits, &x, 4);
+	if (x == 0) return bits == 0;          /* +0 only: see div_hoisted */
+	return a >= 0x1p-37f && a <= 0x1p59f;
 }
 
 static void grow(RtVector3 *lo, RtVector3 *hi, float x, float y, float z)

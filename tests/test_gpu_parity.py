@@ -107,10 +107,23 @@ def test_trace_random_scenes_linear_and_lbvh(renderer, port, seed, n, spheres):
         assert np.array_equal(bits(hit), bits(want_hit))
 
 
+def test_negative_zero_coordinates_take_the_plain_path(renderer, port, small_sky):
+    """A box coordinate of -0 is outside the hoisted-division guard (the sign of
+    a zero quotient); such scenes must still match the oracle."""
+    objs = host.parse_scene_string("cube origin {-0 0 5} size {5 1 1}\ncube origin {4 -0 -0} size {1 3 3}\nsphere center {5 1 3} radius 1")
+    assert np.signbit(objs[0]["geom"][0]) and np.signbit(objs[1]["geom"][1])
+    renderer.upload_skybox(small_sky)
+    renderer.upload_scene(objs)
+    cam = Camera((0.0, 5.0, 0.0), (1.0, -1.0, 1.0), (0, 1, 0), 30.0)      # origin components exactly +0
+    frame, st = renderer.render_frame(cam, 160, 90, 1)
+    want, rays = port.render(port.world(objs, small_sky, cam.as_dict()), 160, 90, 1, 1, 0)
+    assert np.array_equal(bits(frame), bits(want)) and st["rays"] == rays
+
+
 def test_hoisted_division_is_ieee(renderer):
     """The slab test divides by a per-ray refined reciprocal (rt_device.cuh:
     div_hoisted); inside the guarded operand range it must equal IEEE a / b bit
-    for bit.  ~1.2e9 operand pairs incl. all-ones / all-zeros mantissas, +-0."""
+    for bit.  ~1.2e9 operand pairs incl. all-ones / all-zeros mantissas and +0 numerators."""
     assert renderer.div_check(1, 148 * 8, 1024) == 0                       # the guarded range
     assert renderer.div_check(2, 148 * 8, 1024, -40, -38, 58, 60) == 0     # largest quotients
     assert renderer.div_check(3, 148 * 8, 1024, 38, 40, -60, -58) == 0     # smallest quotients

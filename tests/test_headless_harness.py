@@ -53,7 +53,7 @@ def test_harness_progressive_frames_match_oracle(tmp_path, port, real_sky):
         count = np.float32(count + np.float32(1.0) / np.float32(s * s))
     want = port.resolve(acc, count)
     assert np.array_equal(bits(got), bits(want))
-    assert abs(info["accum_count"] - float(count)) < 1e-6
+    assert abs(info["accum_count"] - float(count)) < 1e-3      # printed with 4 decimals
 
     # screenshot rule: (uint8_t)(x*255), flipped vertically, P6
     with open(ppm, "rb") as f:
