@@ -236,7 +236,8 @@ def main_gpu(args):
     r.upload_scene(objs)
     cam = host.Camera()
     variant = host.RT_VARIANT_FAST if args.variant == "fast" else host.RT_VARIANT_EXACT
-    kernel = {"auto": host.RT_KERNEL_AUTO, "pixel": host.RT_KERNEL_PIXEL, "persistent": host.RT_KERNEL_PERSISTENT}[args.kernel]
+    kernel = {"auto": host.RT_KERNEL_AUTO, "pixel": host.RT_KERNEL_PIXEL, "persistent": host.RT_KERNEL_PERSISTENT,
+              "wavefront": host.RT_KERNEL_WAVEFRONT}[args.kernel]
 
     r0, r1 = band_rows(H, 1, rank, world)
     band = torch.empty((max(r1 - r0, 1), W, 3), dtype=torch.float32, device=dev)
@@ -448,7 +449,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--variant", default="exact", choices=["exact", "fast"])
-    ap.add_argument("--kernel", default="auto", choices=["auto", "pixel", "persistent"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "pixel", "persistent", "wavefront"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--composite", default="p2p", choices=["p2p", "nccl"], help="N>1: how bands reach rank 0")
     args = ap.parse_args()

@@ -27,6 +27,8 @@
 #define DECLARE_VARIANT(ns)                                                                              \
 	extern "C" cudaError_t ns##_launch_render(const RtRenderParams *, int, int, int, cudaStream_t);      \
 	extern "C" cudaError_t ns##_persistent_blocks_per_sm(const RtRenderParams *, int, int *);            \
+	extern "C" cudaError_t ns##_wavefront_blocks_per_sm(const RtRenderParams *, int, int *);             \
+	extern "C" int ns##_wavefront_paths_per_block(void);                                                \
 	extern "C" cudaError_t ns##_launch_probe_trace(const RtRenderParams *, int, const float *, int,      \
 	                                               float *, int *, cudaStream_t);                        \
 	extern "C" cudaError_t ns##_launch_probe_sky(const RtSkyView *, const float *, const float *, int,   \
@@ -439,7 +441,7 @@ extern "C" float rt_cuda_accum_count(void) { return g.accum_count; }
 struct PassPlan {
 	int  w, h, scale, ncols;
 	int  row0, row1;          /* output band of the whole call */
-	bool lbvh, persistent, exact;
+	bool lbvh, persistent, exact, wavefront;
 };
 
 /* Rows of a band are dealt to GPUs (or ranks) in blocks of RT_INTERLEAVE_ROWS
@@ -549,6 +551,22 @@ static int launch_band(DeviceCtx &d, const RtCamera *cam, const PassPlan &pl, co
 
 	if (P.tiles_x > 0 && P.tiles_y > 0) {
 		int grid = 0;
+		if (pl.wavefront) {
+			CU(cudaMemsetAsync(d.work_counter, 0, sizeof(unsigned int), stream));
+			static int wf_per_sm[2][2] = {{0, 0}, {0, 0}}, wf_n[2][2] = {{-1, -1}, {-1, -1}};
+			int &per_sm = wf_per_sm[pl.exact ? 0 : 1][pl.lbvh ? 1 : 0];
+			int &for_n = wf_n[pl.exact ? 0 : 1][pl.lbvh ? 1 : 0];
+			if (per_sm < 1 || for_n != P.scene.n) {
+				CU((pl.exact ? rt_exact_wavefront_blocks_per_sm : rt_fast_wavefront_blocks_per_sm)(&P, pl.lbvh, &per_sm));
+				if (per_sm < 1) return fail(RT_ERR_ARG, "the wavefront kernel does not fit: %d objects staged next to the path pool", P.scene.n);
+				for_n = P.scene.n;
+			}
+			unsigned paths = (unsigned) rt_exact_wavefront_paths_per_block();
+			unsigned pixels = (unsigned) P.tiles_x * P.tiles_y * 32u;
+			grid = (int) std::min<unsigned>((unsigned) (d.sm_count * per_sm), (pixels + paths - 1) / paths);
+			CU((pl.exact ? rt_exact_launch_render : rt_fast_launch_render)(&P, pl.lbvh, 2, grid, stream));
+			(*launches)++;
+		} else {
 		if (pl.persistent) {
 			CU(cudaMemsetAsync(d.work_counter, 0, sizeof(unsigned int), stream));
 			/* occupancy of the persistent kernel, queried once per (variant, traversal, scene size) */
@@ -566,6 +584,7 @@ static int launch_band(DeviceCtx &d, const RtCamera *cam, const PassPlan &pl, co
 		}
 		CU((pl.exact ? rt_exact_launch_render : rt_fast_launch_render)(&P, pl.lbvh, pl.persistent, grid, stream));
 		(*launches)++;
+		}
 	}
 
 	return RT_OK;
@@ -599,6 +618,7 @@ static int render_pass(const RtCamera *cam, void *fb, int w, int h, const RtRend
 	if (rc != RT_OK) return rc;
 	pl.exact = o->variant == RT_VARIANT_EXACT;
 	pl.persistent = o->kernel == RT_KERNEL_PERSISTENT || (o->kernel == RT_KERNEL_AUTO);
+	pl.wavefront = o->kernel == RT_KERNEL_WAVEFRONT;
 
 	size_t bpp = bytes_per_pixel(o->fb_format);
 	int band_rows = pl.row1 - pl.row0;

@@ -267,6 +267,302 @@ render_persistent_kernel(const __grid_constant__ RtRenderParams P)
 	count_rays(P, rays);
 }
 
+/* ------------------------------------------------------- wavefront kernel */
+
+/*
+ * render_wavefront_kernel: the same per-path state machine, but the paths of a
+ * CTA live in a SHARED-MEMORY pool (structure of arrays, 32 words per path) and
+ * every phase of a round runs over a compacted list of exactly the paths that
+ * need it, 32 at a time:
+ *
+ *   refill   idle slots store their finished pixel and take the next pixel
+ *   trace    paths with a pending ray: nearest-hit scan + classify
+ *   sweep    three rd.n > 0 tests per fresh surface (one task per lane)
+ *   launch   paths with a surface: next shadow ray, or shade and bounce
+ *
+ * In the persistent kernel a lane owns one path, so whenever some lanes of a
+ * warp need a phase the whole warp walks through it (ncu: 15 of 32 lanes active
+ * per instruction; the non-trace phases ran at 25-40 % of lanes).  Here a warp
+ * only ever executes a phase with lanes that need it.  Per-path arithmetic and
+ * the order of every path's own draws are unchanged, so results are identical.
+ */
+#define WF_THREADS 256          /* 8 warps; three CTAs per SM = 24 warps */
+#define WF_PATHS   512          /* two pool slots per thread: tid and tid + WF_THREADS */
+#define WF_WORDS   32
+#define WF_NW      (WF_THREADS / 32)
+
+enum { WF_RO = 0, WF_RD = 3, WF_D = 6, WF_CONTRIB = 9, WF_RESULT = 12, WF_POINT = 15, WF_NORMAL = 18,
+       WF_TOLIGHT = 21, WF_SAMPLED = 24, WF_RNGLO = 27, WF_RNGHI = 28, WF_OBJ = 29, WF_STATE = 30, WF_PIXEL = 31 };
+
+/* WF_STATE bits */
+#define WF_MODE(st)      ((st) & 3u)
+#define WF_SHADOW        (1u << 2)
+#define WF_OWNS          (1u << 3)
+#define WF_BOUNCE(st)    (((st) >> 4) & 15u)
+#define WF_GOT(st)       (((st) >> 8) & 3u)
+#define WF_PENDING(st)   (((st) >> 10) & 7u)
+#define WF_FRESH         (1u << 13)
+#define WF_SKY           (1u << 14)     /* idle slot whose path escaped: sky lookup pending (direction in WF_POINT) */
+#define WF_TW(st)        (((st) >> 16) & 31u)
+
+struct WfPool {
+	float *w;
+	__device__ __forceinline__ float &f(int field, int slot) const { return w[field * WF_PATHS + slot]; }
+	__device__ __forceinline__ unsigned &u(int field, int slot) const { return reinterpret_cast<unsigned *>(w)[field * WF_PATHS + slot]; }
+	__device__ __forceinline__ f3 get3(int field, int slot) const { return mk(f(field, slot), f(field + 1, slot), f(field + 2, slot)); }
+	__device__ __forceinline__ void set3(int field, int slot, f3 v) const { f(field, slot) = v.x; f(field + 1, slot) = v.y; f(field + 2, slot) = v.z; }
+};
+
+/*
+ * K-way compaction (K <= 4) of the CTA's slots, two per thread: slot j of the
+ * thread goes to list k if pred[k][j].  One pass, two barriers; counts[k]
+ * receives the totals.  All threads must call; a trailing barrier is the
+ * caller's business.
+ */
+template <int K>
+__device__ __forceinline__ void wf_compact(const bool (&pred)[K][2], int *const (&lists)[K], int *warp_off, int *counts)
+{
+	const unsigned full = 0xffffffffu;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	unsigned m[K][2];
+#pragma unroll
+	for (int k = 0; k < K; k++) {
+		m[k][0] = __ballot_sync(full, pred[k][0]);
+		m[k][1] = __ballot_sync(full, pred[k][1]);
+		if (lane == 0) warp_off[k * WF_NW + warp] = __popc(m[k][0]) + __popc(m[k][1]);
+	}
+	__syncthreads();
+	if (warp == 0) {
+		/* exclusive scans of the WF_NW (= 8) per-warp counts, one list per 8 lanes */
+		int seg = lane >> 3, idx = lane & 7;
+		int v = seg < K ? warp_off[seg * WF_NW + idx] : 0;
+		int incl = v;
+#pragma unroll
+		for (int o = 1; o < 8; o <<= 1) {
+			int t = __shfl_up_sync(full, incl, o, 8);
+			if (idx >= o) incl += t;
+		}
+		if (seg < K) {
+			warp_off[seg * WF_NW + idx] = incl - v;
+			if (idx == WF_NW - 1) counts[seg] = incl;
+		}
+	}
+	__syncthreads();
+	unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+	for (int k = 0; k < K; k++) {
+		int base = warp_off[k * WF_NW + warp];
+		if (pred[k][0]) lists[k][base + __popc(m[k][0] & lt)] = threadIdx.x;
+		if (pred[k][1]) lists[k][base + __popc(m[k][0]) + __popc(m[k][1] & lt)] = threadIdx.x + WF_THREADS;
+	}
+}
+
+/* launch for one pool slot; SHADE_ONLY / SHADOW_ONLY lists run a specialised body */
+__device__ __forceinline__ void wf_launch_slot(const WfPool &pool, int s, const RtSceneView &scene)
+{
+	unsigned st = pool.u(WF_STATE, s);
+	Path p;
+	p.mode = MODE_LAUNCH;
+	p.rng = ((uint64_t) pool.u(WF_RNGHI, s) << 32) | pool.u(WF_RNGLO, s);
+	p.pending = (int) WF_PENDING(st);
+	p.got = (st & WF_FRESH) ? __popc(WF_PENDING(st)) : (int) WF_GOT(st);   /* main.c:206 */
+	p.bounce = (int) WF_BOUNCE(st);
+	p.shadow = (st & WF_SHADOW) != 0;
+	p.normal = pool.get3(WF_NORMAL, s);
+	p.point = pool.get3(WF_POINT, s);
+	p.to_light = pool.get3(WF_TOLIGHT, s);
+	const bool shade = p.pending == 0;
+	if (shade) {
+		p.obj = (int) pool.u(WF_OBJ, s);
+		p.sampled = pool.get3(WF_SAMPLED, s);
+		p.d = pool.get3(WF_D, s);
+		p.contrib = pool.get3(WF_CONTRIB, s);
+		p.result = pool.get3(WF_RESULT, s);
+	}
+	uint64_t rng_before = p.rng;
+	path_launch(p, scene);
+	pool.set3(WF_RO, s, p.ray_o);
+	pool.set3(WF_RD, s, p.ray_d);
+	if (shade) {
+		pool.set3(WF_D, s, p.d);
+		pool.set3(WF_CONTRIB, s, p.contrib);
+		pool.set3(WF_RESULT, s, p.result);
+		if (p.rng != rng_before) {
+			pool.u(WF_RNGLO, s) = (unsigned) p.rng;
+			pool.u(WF_RNGHI, s) = (unsigned) (p.rng >> 32);
+		}
+	}
+	pool.u(WF_STATE, s) = (st & (WF_OWNS | (31u << 16))) | (unsigned) p.mode | (p.shadow ? WF_SHADOW : 0u) |
+	                      ((unsigned) p.bounce << 4) | ((unsigned) p.got << 8) | ((unsigned) p.pending << 10);
+}
+
+template <bool LBVH>
+__global__ void __launch_bounds__(WF_THREADS, 3)
+render_wavefront_kernel(const __grid_constant__ RtRenderParams P)
+{
+	extern __shared__ __align__(16) unsigned char smem[];
+	SharedScene S = stage_scene(P, smem, !LBVH);
+	size_t scene_bytes = 256 * sizeof(float) + RT_BLOCK_THREADS +
+	                     (LBVH ? 0 : 2 * sizeof(float4) * (size_t) P.scene.n + sizeof(int2) * (size_t) P.scene.num_runs);
+	scene_bytes = (scene_bytes + 15) & ~(size_t) 15;
+	WfPool pool;
+	pool.w = reinterpret_cast<float *>(smem + scene_bytes);
+	int *list0 = reinterpret_cast<int *>(pool.w + WF_WORDS * WF_PATHS);
+	int *list1 = list0 + WF_PATHS;
+	int *list2 = list1 + WF_PATHS;
+	__shared__ int warp_off[4 * WF_NW];
+	__shared__ int counts[4];
+	__shared__ unsigned claim_base;
+
+	const unsigned total = (unsigned) (P.tiles_x * P.tiles_y) * 32u;
+	const bool lit = P.scene.light_index >= 0;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int s0 = threadIdx.x, s1 = threadIdx.x + WF_THREADS;
+	unsigned rays = 0;
+	bool exhausted = false;          /* CTA-uniform */
+
+	pool.u(WF_STATE, s0) = 0u;
+	pool.u(WF_STATE, s1) = 0u;
+	__syncthreads();
+
+	for (;;) {
+		/* ---- lists of this round: slots with a pending ray (0) and idle slots (1) ---- */
+		unsigned st0 = pool.u(WF_STATE, s0), st1 = pool.u(WF_STATE, s1);
+		{
+			const bool pred[2][2] = {{WF_MODE(st0) == MODE_TRACE, WF_MODE(st1) == MODE_TRACE},
+			                         {WF_MODE(st0) == MODE_IDLE, WF_MODE(st1) == MODE_IDLE}};
+			int *const lists[2] = {list0, list1};
+			wf_compact<2>(pred, lists, warp_off, counts);
+		}
+		if (threadIdx.x == 0 && !exhausted && counts[1] > 0) claim_base = atomicAdd(P.work_counter, (unsigned) counts[1]);
+		__syncthreads();
+		int n_trace = counts[0], n_idle = counts[1];
+		unsigned base = claim_base;
+		if (!exhausted && n_idle > 0 && base >= total) exhausted = true;
+
+		/* ---- idle slots: finish the escaped path (sky), hand in the pixel, take the next one ---- */
+		for (int i = threadIdx.x; i < n_idle; i += WF_THREADS) {
+			int s = list1[i];
+			unsigned st = pool.u(WF_STATE, s);
+			if (st & WF_OWNS) {
+				f3 res = pool.get3(WF_RESULT, s);
+				if (st & WF_SKY) {                          /* main.c:170-171 */
+					f3 skyc = sky_lookup(P.sky, S.lut, pool.get3(WF_POINT, s));
+					res = add3(res, mul3(skyc, pool.get3(WF_CONTRIB, s)));
+				}
+				Cell c;
+				unsigned px = pool.u(WF_PIXEL, s);
+				c.x0 = (int) (px & 0xffffu); c.y0 = (int) (px >> 16); c.tw = (int) WF_TW(st);
+				store_cell(P, c, mk(clamp01(res.x), clamp01(res.y), clamp01(res.z)));
+			}
+			unsigned idx = base + (unsigned) i;
+			int cx, cy;
+			bool ok = !exhausted && idx < total && cell_of(P, idx, cx, cy);
+			if (ok) {
+				Cell c = cell_geometry(P, cx, cy);
+				Path p;
+				path_begin(p, P.cam, c.u, c.v, P.pass_mix);
+				pool.set3(WF_RO, s, p.ray_o);
+				pool.set3(WF_RD, s, p.ray_d);
+				pool.set3(WF_D, s, p.d);
+				pool.set3(WF_CONTRIB, s, p.contrib);
+				pool.set3(WF_RESULT, s, p.result);
+				pool.u(WF_RNGLO, s) = (unsigned) p.rng;
+				pool.u(WF_RNGHI, s) = (unsigned) (p.rng >> 32);
+				pool.u(WF_PIXEL, s) = (unsigned) c.x0 | ((unsigned) c.y0 << 16);
+				pool.u(WF_STATE, s) = (unsigned) MODE_TRACE | WF_OWNS | ((unsigned) c.tw << 16);
+			} else
+				pool.u(WF_STATE, s) = 0u;
+			/* refilled slots join this round's trace list (-1 = nothing dealt) */
+			list0[n_trace + i] = ok ? s : -1;
+		}
+		n_trace += n_idle;
+		__syncthreads();
+		{
+			/* anything left in flight? (clipped cells and exhausted work leave idle slots) */
+			bool busy = false;
+			for (int i = threadIdx.x; i < n_trace && !busy; i += WF_THREADS) busy = list0[i] >= 0;
+			unsigned a0 = pool.u(WF_STATE, s0), a1 = pool.u(WF_STATE, s1);
+			busy = busy || WF_MODE(a0) == MODE_LAUNCH || WF_MODE(a1) == MODE_LAUNCH;
+			if (!__syncthreads_or(busy)) {
+				if (exhausted) break;
+				continue;
+			}
+		}
+
+		/* ---------------- trace + classify ---------------- */
+		for (int c0 = warp * 32; c0 < n_trace; c0 += WF_NW * 32) {
+			int i = c0 + lane;
+			int s = i < n_trace ? list0[i] : -1;
+			if (s >= 0) {
+				unsigned st = pool.u(WF_STATE, s);
+				f3 ro = pool.get3(WF_RO, s);
+				f3 dn = unit3(pool.get3(WF_RD, s));  /* scene.c:158 */
+				RayQ q = ray_quadratic(dn);
+				Hit h;
+				if (LBVH) h = nearest_lbvh(P.bvh, P.scene.geomA, P.scene.geomB, ro, dn, q);
+				else      h = nearest_linear(S.A, S.B, S.runs, P.scene.num_runs, P.scene.n, ro, dn, q, P.scene.div_safe);
+				rays++;
+				if (st & WF_SHADOW) {
+					if (h.obj >= 0) {                      /* main.c:201-204 */
+						float4 m2 = __ldg(P.scene.mat + (size_t) h.obj * RT_MAT_STRIDE + 2);
+						pool.set3(WF_SAMPLED, s, add3(pool.get3(WF_SAMPLED, s), mk(m2.x, m2.y, m2.z)));
+					}
+					pool.u(WF_STATE, s) = (st & ~3u) | (unsigned) MODE_LAUNCH;
+				} else if (h.obj < 0) {
+					/* escaped: the sky lookup runs with the idle list of the next round */
+					pool.set3(WF_POINT, s, dn);
+					pool.u(WF_STATE, s) = (st & ~3u) | (unsigned) MODE_IDLE | WF_SKY;
+				} else {
+					f3 point, normal;
+					if (LBVH) surface_of(h, __ldg(&P.scene.geomA[h.obj]), __ldg(&P.scene.geomB[h.obj]), ro, dn, point, normal);
+					else      surface_of(h, S.A[h.obj], S.B[h.obj], ro, dn, point, normal);
+					pool.u(WF_OBJ, s) = (unsigned) h.obj;
+					pool.set3(WF_POINT, s, point);
+					pool.set3(WF_NORMAL, s, normal);
+					pool.set3(WF_SAMPLED, s, mk(0.0f, 0.0f, 0.0f));
+					if (lit) pool.set3(WF_TOLIGHT, s, sub3(mk(P.scene.light_pos), point));   /* main.c:184 */
+					/* got = 0, pending = 0; fresh asks the sweep phase for the three tests */
+					pool.u(WF_STATE, s) = (st & ~(3u | (3u << 8) | (7u << 10) | WF_FRESH)) | (unsigned) MODE_LAUNCH | (lit ? WF_FRESH : 0u);
+				}
+			}
+		}
+		__syncthreads();
+
+		/* ---- lists after the trace: fresh surfaces (0), next shadow ray (1), shade (2) ---- */
+		st0 = pool.u(WF_STATE, s0); st1 = pool.u(WF_STATE, s1);
+		{
+			const bool l0 = WF_MODE(st0) == MODE_LAUNCH, l1 = WF_MODE(st1) == MODE_LAUNCH;
+			const bool f0 = l0 && (st0 & WF_FRESH), f1 = l1 && (st1 & WF_FRESH);
+			const bool pred[3][2] = {{f0, f1},
+			                         {l0 && !f0 && WF_PENDING(st0) != 0, l1 && !f1 && WF_PENDING(st1) != 0},
+			                         {l0 && !f0 && WF_PENDING(st0) == 0, l1 && !f1 && WF_PENDING(st1) == 0}};
+			int *const lists[3] = {list0, list1, list2};
+			wf_compact<3>(pred, lists, warp_off, counts);
+		}
+		__syncthreads();
+		int n_fresh = counts[0], n_shadow = counts[1], n_shade = counts[2];
+
+		/* ---------------- sweep: three tests per fresh surface, one per lane ---------------- */
+		for (int t = threadIdx.x; t < 3 * n_fresh; t += WF_THREADS) {
+			int j = (int) (((unsigned) t * 43691u) >> 17);     /* t / 3 for t < 98304 */
+			int k = t - 3 * j;
+			int s = list0[j];
+			uint64_t x0 = ((uint64_t) pool.u(WF_RNGHI, s) << 32) | pool.u(WF_RNGLO, s);
+			if (sample_faces_surface(x0, k, pool.get3(WF_NORMAL, s), P.sweep_tau2))
+				atomicOr(&pool.u(WF_STATE, s), 1u << (10 + k));
+		}
+		/* ---------------- launch: homogeneous lists first (no dependence on the sweep) ---------------- */
+		for (int i = threadIdx.x; i < n_shadow; i += WF_THREADS) wf_launch_slot(pool, list1[i], P.scene);
+		for (int i = threadIdx.x; i < n_shade; i += WF_THREADS) wf_launch_slot(pool, list2[i], P.scene);
+		__syncthreads();
+		/* fresh surfaces: 7 of 8 have a sample that faces the surface, so mostly shadow rays */
+		for (int i = threadIdx.x; i < n_fresh; i += WF_THREADS) wf_launch_slot(pool, list0[i], P.scene);
+		__syncthreads();
+	}
+	count_rays(P, rays);
+}
+
 /* ------------------------------------------------------------ unit probes */
 
 template <bool LBVH>
@@ -379,6 +675,12 @@ static cudaError_t allow_smem(K kernel, size_t bytes)
 	return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
 }
 
+static size_t wavefront_smem_bytes(const RtRenderParams &P, bool lbvh)
+{
+	size_t scene = (smem_bytes(P, lbvh) + 15) & ~(size_t) 15;
+	return scene + sizeof(float) * WF_WORDS * WF_PATHS + 3 * sizeof(int) * WF_PATHS;
+}
+
 extern "C" cudaError_t RT_FN(launch_render)(const RtRenderParams *P, int lbvh, int persistent,
                                              int grid_blocks, cudaStream_t stream)
 {
@@ -387,6 +689,17 @@ extern "C" cudaError_t RT_FN(launch_render)(const RtRenderParams *P, int lbvh, i
 	unsigned total = (unsigned) (P->tiles_x * P->tiles_y) * 32u;
 	if (total == 0) return cudaSuccess;
 	cudaError_t e;
+	if (persistent == 2) {      /* wavefront kernel: one CTA per SM, paths pooled in shared memory */
+		size_t wsm = wavefront_smem_bytes(*P, lbvh != 0);
+		if (lbvh) {
+			if ((e = allow_smem(render_wavefront_kernel<true>, wsm)) != cudaSuccess) return e;
+			render_wavefront_kernel<true><<<grid_blocks, WF_THREADS, wsm, stream>>>(*P);
+		} else {
+			if ((e = allow_smem(render_wavefront_kernel<false>, wsm)) != cudaSuccess) return e;
+			render_wavefront_kernel<false><<<grid_blocks, WF_THREADS, wsm, stream>>>(*P);
+		}
+		return cudaGetLastError();
+	}
 	if (persistent) {
 		if (lbvh) {
 			if ((e = allow_smem(render_persistent_kernel<true>, sm)) != cudaSuccess) return e;
@@ -407,6 +720,21 @@ extern "C" cudaError_t RT_FN(launch_render)(const RtRenderParams *P, int lbvh, i
 	}
 	return cudaGetLastError();
 }
+
+extern "C" cudaError_t RT_FN(wavefront_blocks_per_sm)(const RtRenderParams *P, int lbvh, int *out)
+{
+	using namespace RT_NS;
+	size_t sm = wavefront_smem_bytes(*P, lbvh != 0);
+	cudaError_t e;
+	if (lbvh) {
+		if ((e = allow_smem(render_wavefront_kernel<true>, sm)) != cudaSuccess) return e;
+		return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, render_wavefront_kernel<true>, WF_THREADS, sm);
+	}
+	if ((e = allow_smem(render_wavefront_kernel<false>, sm)) != cudaSuccess) return e;
+	return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, render_wavefront_kernel<false>, WF_THREADS, sm);
+}
+
+extern "C" int RT_FN(wavefront_paths_per_block)(void) { return WF_PATHS; }
 
 /* occupancy query for sizing the persistent grid */
 extern "C" cudaError_t RT_FN(persistent_blocks_per_sm)(const RtRenderParams *P, int lbvh, int *out)

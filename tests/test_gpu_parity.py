@@ -14,12 +14,12 @@ import pytest
 
 from conftest import GOLDEN, random_scene
 from ray_tracing_b200 import host, scenes
-from ray_tracing_b200.host import (RT_FB_U8X4, RT_KERNEL_PERSISTENT, RT_KERNEL_PIXEL, RT_TRAVERSAL_LBVH,
+from ray_tracing_b200.host import (RT_FB_U8X4, RT_KERNEL_PERSISTENT, RT_KERNEL_PIXEL, RT_KERNEL_WAVEFRONT, RT_TRAVERSAL_LBVH,
                                    RT_TRAVERSAL_LINEAR, RT_VARIANT_EXACT, RT_VARIANT_FAST, Camera)
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = [RT_KERNEL_PIXEL, RT_KERNEL_PERSISTENT]
+KERNELS = [RT_KERNEL_PIXEL, RT_KERNEL_PERSISTENT, RT_KERNEL_WAVEFRONT]
 
 
 def bits(a):
@@ -423,6 +423,8 @@ def test_lbvh_equals_linear_scan_frames(renderer, small_sky):
     a, sa = renderer.render_frame(Camera(), 480, 270, 1, traversal=RT_TRAVERSAL_LINEAR)
     b, sb = renderer.render_frame(Camera(), 480, 270, 1, traversal=RT_TRAVERSAL_LBVH)
     assert np.array_equal(bits(a), bits(b)) and sa["rays"] == sb["rays"]
+    c, sc = renderer.render_frame(Camera(), 480, 270, 1, traversal=RT_TRAVERSAL_LBVH, kernel=RT_KERNEL_WAVEFRONT)
+    assert np.array_equal(bits(a), bits(c)) and sa["rays"] == sc["rays"]
 
 
 def test_large_scene_lbvh_vs_oracle(renderer, port, small_sky):
