@@ -270,26 +270,29 @@ render_persistent_kernel(const __grid_constant__ RtRenderParams P)
 /* ------------------------------------------------------- wavefront kernel */
 
 /*
- * render_wavefront_kernel: the same per-path state machine, but the paths of a
- * CTA live in a SHARED-MEMORY pool (structure of arrays, 32 words per path) and
- * every phase of a round runs over a compacted list of exactly the paths that
- * need it, 32 at a time:
+ * render_wavefront_kernel: the same per-path state machine, but every WARP
+ * keeps a pool of 64 paths in SHARED MEMORY (structure of arrays, 32 words per
+ * path) and runs each phase of a round over a compacted list of exactly the
+ * paths that need it, 32 at a time:
  *
- *   refill   idle slots store their finished pixel and take the next pixel
+ *   idle     escaped paths finish (sky lookup), pixels are stored, new pixels taken
  *   trace    paths with a pending ray: nearest-hit scan + classify
  *   sweep    three rd.n > 0 tests per fresh surface (one task per lane)
- *   launch   paths with a surface: next shadow ray, or shade and bounce
+ *   launch   next shadow ray / shade and bounce, as separate homogeneous lists
  *
  * In the persistent kernel a lane owns one path, so whenever some lanes of a
  * warp need a phase the whole warp walks through it (ncu: 15 of 32 lanes active
  * per instruction; the non-trace phases ran at 25-40 % of lanes).  Here a warp
- * only ever executes a phase with lanes that need it.  Per-path arithmetic and
- * the order of every path's own draws are unchanged, so results are identical.
+ * executes a phase only with lanes that need it.  Pools are per warp, so the
+ * phases need no CTA barrier (a first version with one pool per CTA executed
+ * 30 % fewer instructions but lost it all to barrier stalls).  Per-path
+ * arithmetic and the order of every path's own draws are unchanged, so the
+ * results are identical to the other kernels'.
  */
-#define WF_THREADS 256          /* 8 warps; three CTAs per SM = 24 warps */
-#define WF_PATHS   512          /* two pool slots per thread: tid and tid + WF_THREADS */
+#define WF_WARPS   4            /* warps per CTA */
+#define WF_THREADS (32 * WF_WARPS)
+#define WF_PATHS   64           /* per warp: two pool slots per lane (lane, lane + 32) */
 #define WF_WORDS   32
-#define WF_NW      (WF_THREADS / 32)
 
 enum { WF_RO = 0, WF_RD = 3, WF_D = 6, WF_CONTRIB = 9, WF_RESULT = 12, WF_POINT = 15, WF_NORMAL = 18,
        WF_TOLIGHT = 21, WF_SAMPLED = 24, WF_RNGLO = 27, WF_RNGHI = 28, WF_OBJ = 29, WF_STATE = 30, WF_PIXEL = 31 };
@@ -306,58 +309,27 @@ enum { WF_RO = 0, WF_RD = 3, WF_D = 6, WF_CONTRIB = 9, WF_RESULT = 12, WF_POINT 
 #define WF_TW(st)        (((st) >> 16) & 31u)
 
 struct WfPool {
-	float *w;
+	float *w;                   /* this warp's pool: WF_WORDS x WF_PATHS words */
 	__device__ __forceinline__ float &f(int field, int slot) const { return w[field * WF_PATHS + slot]; }
 	__device__ __forceinline__ unsigned &u(int field, int slot) const { return reinterpret_cast<unsigned *>(w)[field * WF_PATHS + slot]; }
 	__device__ __forceinline__ f3 get3(int field, int slot) const { return mk(f(field, slot), f(field + 1, slot), f(field + 2, slot)); }
 	__device__ __forceinline__ void set3(int field, int slot, f3 v) const { f(field, slot) = v.x; f(field + 1, slot) = v.y; f(field + 2, slot) = v.z; }
 };
 
-/*
- * K-way compaction (K <= 4) of the CTA's slots, two per thread: slot j of the
- * thread goes to list k if pred[k][j].  One pass, two barriers; counts[k]
- * receives the totals.  All threads must call; a trailing barrier is the
- * caller's business.
- */
-template <int K>
-__device__ __forceinline__ void wf_compact(const bool (&pred)[K][2], int *const (&lists)[K], int *warp_off, int *counts)
+/* Append this lane's two slots (lane, lane + 32) to a warp-local list if their
+ * predicates hold; returns the list length.  Warp-convergent. */
+__device__ __forceinline__ int wf_list(bool p0, bool p1, unsigned char *list)
 {
 	const unsigned full = 0xffffffffu;
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	unsigned m[K][2];
-#pragma unroll
-	for (int k = 0; k < K; k++) {
-		m[k][0] = __ballot_sync(full, pred[k][0]);
-		m[k][1] = __ballot_sync(full, pred[k][1]);
-		if (lane == 0) warp_off[k * WF_NW + warp] = __popc(m[k][0]) + __popc(m[k][1]);
-	}
-	__syncthreads();
-	if (warp == 0) {
-		/* exclusive scans of the WF_NW (= 8) per-warp counts, one list per 8 lanes */
-		int seg = lane >> 3, idx = lane & 7;
-		int v = seg < K ? warp_off[seg * WF_NW + idx] : 0;
-		int incl = v;
-#pragma unroll
-		for (int o = 1; o < 8; o <<= 1) {
-			int t = __shfl_up_sync(full, incl, o, 8);
-			if (idx >= o) incl += t;
-		}
-		if (seg < K) {
-			warp_off[seg * WF_NW + idx] = incl - v;
-			if (idx == WF_NW - 1) counts[seg] = incl;
-		}
-	}
-	__syncthreads();
-	unsigned lt = (1u << lane) - 1u;
-#pragma unroll
-	for (int k = 0; k < K; k++) {
-		int base = warp_off[k * WF_NW + warp];
-		if (pred[k][0]) lists[k][base + __popc(m[k][0] & lt)] = threadIdx.x;
-		if (pred[k][1]) lists[k][base + __popc(m[k][0]) + __popc(m[k][1] & lt)] = threadIdx.x + WF_THREADS;
-	}
+	const unsigned lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
+	unsigned m0 = __ballot_sync(full, p0), m1 = __ballot_sync(full, p1);
+	int n0 = __popc(m0);
+	if (p0) list[__popc(m0 & lt)] = (unsigned char) lane;
+	if (p1) list[n0 + __popc(m1 & lt)] = (unsigned char) (lane + 32);
+	return n0 + __popc(m1);
 }
 
-/* launch for one pool slot; SHADE_ONLY / SHADOW_ONLY lists run a specialised body */
+/* launch for one pool slot: next shadow ray, or shade and bounce */
 __device__ __forceinline__ void wf_launch_slot(const WfPool &pool, int s, const RtSceneView &scene)
 {
 	unsigned st = pool.u(WF_STATE, s);
@@ -396,8 +368,12 @@ __device__ __forceinline__ void wf_launch_slot(const WfPool &pool, int s, const 
 	                      ((unsigned) p.bounce << 4) | ((unsigned) p.got << 8) | ((unsigned) p.pending << 10);
 }
 
+#ifndef RT_WAVEFRONT_MIN_BLOCKS
+#define RT_WAVEFRONT_MIN_BLOCKS 6
+#endif
+
 template <bool LBVH>
-__global__ void __launch_bounds__(WF_THREADS, 3)
+__global__ void __launch_bounds__(WF_THREADS, RT_WAVEFRONT_MIN_BLOCKS)
 render_wavefront_kernel(const __grid_constant__ RtRenderParams P)
 {
 	extern __shared__ __align__(16) unsigned char smem[];
@@ -405,96 +381,93 @@ render_wavefront_kernel(const __grid_constant__ RtRenderParams P)
 	size_t scene_bytes = 256 * sizeof(float) + RT_BLOCK_THREADS +
 	                     (LBVH ? 0 : 2 * sizeof(float4) * (size_t) P.scene.n + sizeof(int2) * (size_t) P.scene.num_runs);
 	scene_bytes = (scene_bytes + 15) & ~(size_t) 15;
+	const unsigned full = 0xffffffffu;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	WfPool pool;
-	pool.w = reinterpret_cast<float *>(smem + scene_bytes);
-	int *list0 = reinterpret_cast<int *>(pool.w + WF_WORDS * WF_PATHS);
-	int *list1 = list0 + WF_PATHS;
-	int *list2 = list1 + WF_PATHS;
-	__shared__ int warp_off[4 * WF_NW];
-	__shared__ int counts[4];
-	__shared__ unsigned claim_base;
+	pool.w = reinterpret_cast<float *>(smem + scene_bytes) + (size_t) warp * WF_WORDS * WF_PATHS;
+	unsigned char *lists = smem + scene_bytes + sizeof(float) * WF_WORDS * WF_PATHS * WF_WARPS + (size_t) warp * 3 * 2 * WF_PATHS;
+	unsigned char *list0 = lists, *list1 = lists + 2 * WF_PATHS, *list2 = lists + 4 * WF_PATHS;   /* list0 may hold trace + refilled */
 
 	const unsigned total = (unsigned) (P.tiles_x * P.tiles_y) * 32u;
 	const bool lit = P.scene.light_index >= 0;
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int s0 = threadIdx.x, s1 = threadIdx.x + WF_THREADS;
+	const int s0 = lane, s1 = lane + 32;
 	unsigned rays = 0;
-	bool exhausted = false;          /* CTA-uniform */
+	bool exhausted = false;          /* warp-uniform */
 
 	pool.u(WF_STATE, s0) = 0u;
 	pool.u(WF_STATE, s1) = 0u;
-	__syncthreads();
+	__syncwarp();
 
 	for (;;) {
 		/* ---- lists of this round: slots with a pending ray (0) and idle slots (1) ---- */
 		unsigned st0 = pool.u(WF_STATE, s0), st1 = pool.u(WF_STATE, s1);
-		{
-			const bool pred[2][2] = {{WF_MODE(st0) == MODE_TRACE, WF_MODE(st1) == MODE_TRACE},
-			                         {WF_MODE(st0) == MODE_IDLE, WF_MODE(st1) == MODE_IDLE}};
-			int *const lists[2] = {list0, list1};
-			wf_compact<2>(pred, lists, warp_off, counts);
+		int n_trace = wf_list(WF_MODE(st0) == MODE_TRACE, WF_MODE(st1) == MODE_TRACE, list0);
+		int n_idle = wf_list(WF_MODE(st0) == MODE_IDLE, WF_MODE(st1) == MODE_IDLE, list1);
+		bool launching = __any_sync(full, WF_MODE(st0) == MODE_LAUNCH || WF_MODE(st1) == MODE_LAUNCH);
+		unsigned base = 0;
+		if (!exhausted && n_idle > 0) {
+			if (lane == 0) base = atomicAdd(P.work_counter, (unsigned) n_idle);
+			base = __shfl_sync(full, base, 0);
+			if (base >= total) exhausted = true;
 		}
-		if (threadIdx.x == 0 && !exhausted && counts[1] > 0) claim_base = atomicAdd(P.work_counter, (unsigned) counts[1]);
-		__syncthreads();
-		int n_trace = counts[0], n_idle = counts[1];
-		unsigned base = claim_base;
-		if (!exhausted && n_idle > 0 && base >= total) exhausted = true;
+		__syncwarp();
 
 		/* ---- idle slots: finish the escaped path (sky), hand in the pixel, take the next one ---- */
-		for (int i = threadIdx.x; i < n_idle; i += WF_THREADS) {
-			int s = list1[i];
-			unsigned st = pool.u(WF_STATE, s);
-			if (st & WF_OWNS) {
-				f3 res = pool.get3(WF_RESULT, s);
-				if (st & WF_SKY) {                          /* main.c:170-171 */
-					f3 skyc = sky_lookup(P.sky, S.lut, pool.get3(WF_POINT, s));
-					res = add3(res, mul3(skyc, pool.get3(WF_CONTRIB, s)));
+		int dealt = 0;
+		for (int c0 = 0; c0 < n_idle; c0 += 32) {
+			int i = c0 + lane;
+			bool ok = false;
+			int s = 0;
+			if (i < n_idle) {
+				s = list1[i];
+				unsigned st = pool.u(WF_STATE, s);
+				if (st & WF_OWNS) {
+					f3 res = pool.get3(WF_RESULT, s);
+					if (st & WF_SKY) {                      /* main.c:170-171 */
+						f3 skyc = sky_lookup(P.sky, S.lut, pool.get3(WF_POINT, s));
+						res = add3(res, mul3(skyc, pool.get3(WF_CONTRIB, s)));
+					}
+					Cell c;
+					unsigned px = pool.u(WF_PIXEL, s);
+					c.x0 = (int) (px & 0xffffu); c.y0 = (int) (px >> 16); c.tw = (int) WF_TW(st);
+					store_cell(P, c, mk(clamp01(res.x), clamp01(res.y), clamp01(res.z)));
 				}
-				Cell c;
-				unsigned px = pool.u(WF_PIXEL, s);
-				c.x0 = (int) (px & 0xffffu); c.y0 = (int) (px >> 16); c.tw = (int) WF_TW(st);
-				store_cell(P, c, mk(clamp01(res.x), clamp01(res.y), clamp01(res.z)));
+				unsigned idx = base + (unsigned) i;
+				int cx, cy;
+				ok = !exhausted && idx < total && cell_of(P, idx, cx, cy);
+				if (ok) {
+					Cell c = cell_geometry(P, cx, cy);
+					Path p;
+					path_begin(p, P.cam, c.u, c.v, P.pass_mix);
+					pool.set3(WF_RO, s, p.ray_o);
+					pool.set3(WF_RD, s, p.ray_d);
+					pool.set3(WF_D, s, p.d);
+					pool.set3(WF_CONTRIB, s, p.contrib);
+					pool.set3(WF_RESULT, s, p.result);
+					pool.u(WF_RNGLO, s) = (unsigned) p.rng;
+					pool.u(WF_RNGHI, s) = (unsigned) (p.rng >> 32);
+					pool.u(WF_PIXEL, s) = (unsigned) c.x0 | ((unsigned) c.y0 << 16);
+					pool.u(WF_STATE, s) = (unsigned) MODE_TRACE | WF_OWNS | ((unsigned) c.tw << 16);
+				} else
+					pool.u(WF_STATE, s) = 0u;
 			}
-			unsigned idx = base + (unsigned) i;
-			int cx, cy;
-			bool ok = !exhausted && idx < total && cell_of(P, idx, cx, cy);
-			if (ok) {
-				Cell c = cell_geometry(P, cx, cy);
-				Path p;
-				path_begin(p, P.cam, c.u, c.v, P.pass_mix);
-				pool.set3(WF_RO, s, p.ray_o);
-				pool.set3(WF_RD, s, p.ray_d);
-				pool.set3(WF_D, s, p.d);
-				pool.set3(WF_CONTRIB, s, p.contrib);
-				pool.set3(WF_RESULT, s, p.result);
-				pool.u(WF_RNGLO, s) = (unsigned) p.rng;
-				pool.u(WF_RNGHI, s) = (unsigned) (p.rng >> 32);
-				pool.u(WF_PIXEL, s) = (unsigned) c.x0 | ((unsigned) c.y0 << 16);
-				pool.u(WF_STATE, s) = (unsigned) MODE_TRACE | WF_OWNS | ((unsigned) c.tw << 16);
-			} else
-				pool.u(WF_STATE, s) = 0u;
-			/* refilled slots join this round's trace list (-1 = nothing dealt) */
-			list0[n_trace + i] = ok ? s : -1;
+			/* refilled slots join this round's trace list */
+			unsigned m = __ballot_sync(full, ok);
+			if (ok) list0[n_trace + dealt + __popc(m & ((1u << lane) - 1u))] = (unsigned char) s;
+			dealt += __popc(m);
 		}
-		n_trace += n_idle;
-		__syncthreads();
-		{
-			/* anything left in flight? (clipped cells and exhausted work leave idle slots) */
-			bool busy = false;
-			for (int i = threadIdx.x; i < n_trace && !busy; i += WF_THREADS) busy = list0[i] >= 0;
-			unsigned a0 = pool.u(WF_STATE, s0), a1 = pool.u(WF_STATE, s1);
-			busy = busy || WF_MODE(a0) == MODE_LAUNCH || WF_MODE(a1) == MODE_LAUNCH;
-			if (!__syncthreads_or(busy)) {
-				if (exhausted) break;
-				continue;
-			}
+		n_trace += dealt;
+		__syncwarp();
+		if (n_trace == 0 && !launching) {
+			if (exhausted) break;
+			continue;               /* only clipped cells were dealt: claim more */
 		}
 
 		/* ---------------- trace + classify ---------------- */
-		for (int c0 = warp * 32; c0 < n_trace; c0 += WF_NW * 32) {
+		for (int c0 = 0; c0 < n_trace; c0 += 32) {
 			int i = c0 + lane;
-			int s = i < n_trace ? list0[i] : -1;
-			if (s >= 0) {
+			if (i < n_trace) {
+				int s = list0[i];
 				unsigned st = pool.u(WF_STATE, s);
 				f3 ro = pool.get3(WF_RO, s);
 				f3 dn = unit3(pool.get3(WF_RD, s));  /* scene.c:158 */
@@ -527,38 +500,32 @@ render_wavefront_kernel(const __grid_constant__ RtRenderParams P)
 				}
 			}
 		}
-		__syncthreads();
+		__syncwarp();
 
-		/* ---- lists after the trace: fresh surfaces (0), next shadow ray (1), shade (2) ---- */
+		/* ---- after the trace: fresh surfaces get their three tests first ... ---- */
 		st0 = pool.u(WF_STATE, s0); st1 = pool.u(WF_STATE, s1);
-		{
-			const bool l0 = WF_MODE(st0) == MODE_LAUNCH, l1 = WF_MODE(st1) == MODE_LAUNCH;
-			const bool f0 = l0 && (st0 & WF_FRESH), f1 = l1 && (st1 & WF_FRESH);
-			const bool pred[3][2] = {{f0, f1},
-			                         {l0 && !f0 && WF_PENDING(st0) != 0, l1 && !f1 && WF_PENDING(st1) != 0},
-			                         {l0 && !f0 && WF_PENDING(st0) == 0, l1 && !f1 && WF_PENDING(st1) == 0}};
-			int *const lists[3] = {list0, list1, list2};
-			wf_compact<3>(pred, lists, warp_off, counts);
-		}
-		__syncthreads();
-		int n_fresh = counts[0], n_shadow = counts[1], n_shade = counts[2];
-
-		/* ---------------- sweep: three tests per fresh surface, one per lane ---------------- */
-		for (int t = threadIdx.x; t < 3 * n_fresh; t += WF_THREADS) {
-			int j = (int) (((unsigned) t * 43691u) >> 17);     /* t / 3 for t < 98304 */
+		int n_fresh = wf_list((st0 & WF_FRESH) != 0 && WF_MODE(st0) == MODE_LAUNCH,
+		                      (st1 & WF_FRESH) != 0 && WF_MODE(st1) == MODE_LAUNCH, list0);
+		__syncwarp();
+		for (int t = lane; t < 3 * n_fresh; t += 32) {
+			int j = (t * 171) >> 9;                         /* t / 3 for t < 256 */
 			int k = t - 3 * j;
 			int s = list0[j];
 			uint64_t x0 = ((uint64_t) pool.u(WF_RNGHI, s) << 32) | pool.u(WF_RNGLO, s);
 			if (sample_faces_surface(x0, k, pool.get3(WF_NORMAL, s), P.sweep_tau2))
 				atomicOr(&pool.u(WF_STATE, s), 1u << (10 + k));
 		}
-		/* ---------------- launch: homogeneous lists first (no dependence on the sweep) ---------------- */
-		for (int i = threadIdx.x; i < n_shadow; i += WF_THREADS) wf_launch_slot(pool, list1[i], P.scene);
-		for (int i = threadIdx.x; i < n_shade; i += WF_THREADS) wf_launch_slot(pool, list2[i], P.scene);
-		__syncthreads();
-		/* fresh surfaces: 7 of 8 have a sample that faces the surface, so mostly shadow rays */
-		for (int i = threadIdx.x; i < n_fresh; i += WF_THREADS) wf_launch_slot(pool, list0[i], P.scene);
-		__syncthreads();
+		__syncwarp();
+
+		/* ---- ... then one launch list, shadow rays first, shading last, so that the
+		 * chunks of 32 are homogeneous except at the single boundary ---- */
+		st0 = pool.u(WF_STATE, s0); st1 = pool.u(WF_STATE, s1);
+		const bool l0 = WF_MODE(st0) == MODE_LAUNCH, l1 = WF_MODE(st1) == MODE_LAUNCH;
+		int n_shadow = wf_list(l0 && WF_PENDING(st0) != 0, l1 && WF_PENDING(st1) != 0, list1);
+		int n_shade = wf_list(l0 && WF_PENDING(st0) == 0, l1 && WF_PENDING(st1) == 0, list1 + n_shadow);
+		__syncwarp();
+		for (int i = lane; i < n_shadow + n_shade; i += 32) wf_launch_slot(pool, list1[i], P.scene);
+		__syncwarp();
 	}
 	count_rays(P, rays);
 }
@@ -678,7 +645,7 @@ static cudaError_t allow_smem(K kernel, size_t bytes)
 static size_t wavefront_smem_bytes(const RtRenderParams &P, bool lbvh)
 {
 	size_t scene = (smem_bytes(P, lbvh) + 15) & ~(size_t) 15;
-	return scene + sizeof(float) * WF_WORDS * WF_PATHS + 3 * sizeof(int) * WF_PATHS;
+	return scene + (sizeof(float) * WF_WORDS * WF_PATHS + 3 * 2 * WF_PATHS) * WF_WARPS;
 }
 
 extern "C" cudaError_t RT_FN(launch_render)(const RtRenderParams *P, int lbvh, int persistent,
@@ -734,7 +701,7 @@ extern "C" cudaError_t RT_FN(wavefront_blocks_per_sm)(const RtRenderParams *P, i
 	return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, render_wavefront_kernel<false>, WF_THREADS, sm);
 }
 
-extern "C" int RT_FN(wavefront_paths_per_block)(void) { return WF_PATHS; }
+extern "C" int RT_FN(wavefront_paths_per_block)(void) { return WF_PATHS * WF_WARPS; }
 
 /* occupancy query for sizing the persistent grid */
 extern "C" cudaError_t RT_FN(persistent_blocks_per_sm)(const RtRenderParams *P, int lbvh, int *out)
