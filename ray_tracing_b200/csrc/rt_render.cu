@@ -291,7 +291,10 @@ render_persistent_kernel(const __grid_constant__ RtRenderParams P)
  */
 #define WF_WARPS   4            /* warps per CTA */
 #define WF_THREADS (32 * WF_WARPS)
-#define WF_PATHS   64           /* per warp: two pool slots per lane (lane, lane + 32) */
+#ifndef WF_SLOTS
+#define WF_SLOTS   2            /* pool slots per lane: lane, lane + 32, ... */
+#endif
+#define WF_PATHS   (32 * WF_SLOTS)   /* paths per warp */
 #define WF_WORDS   32
 
 enum { WF_RO = 0, WF_RD = 3, WF_D = 6, WF_CONTRIB = 9, WF_RESULT = 12, WF_POINT = 15, WF_NORMAL = 18,
@@ -316,17 +319,20 @@ struct WfPool {
 	__device__ __forceinline__ void set3(int field, int slot, f3 v) const { f(field, slot) = v.x; f(field + 1, slot) = v.y; f(field + 2, slot) = v.z; }
 };
 
-/* Append this lane's two slots (lane, lane + 32) to a warp-local list if their
- * predicates hold; returns the list length.  Warp-convergent. */
-__device__ __forceinline__ int wf_list(bool p0, bool p1, unsigned char *list)
+/* Append this lane's slots (lane, lane + 32, ...) whose predicate holds to a
+ * warp-local list; returns the list length.  Warp-convergent. */
+__device__ __forceinline__ int wf_list(const bool (&p)[WF_SLOTS], unsigned char *list)
 {
 	const unsigned full = 0xffffffffu;
 	const unsigned lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
-	unsigned m0 = __ballot_sync(full, p0), m1 = __ballot_sync(full, p1);
-	int n0 = __popc(m0);
-	if (p0) list[__popc(m0 & lt)] = (unsigned char) lane;
-	if (p1) list[n0 + __popc(m1 & lt)] = (unsigned char) (lane + 32);
-	return n0 + __popc(m1);
+	int n = 0;
+#pragma unroll
+	for (int k = 0; k < WF_SLOTS; k++) {
+		unsigned m = __ballot_sync(full, p[k]);
+		if (p[k]) list[n + __popc(m & lt)] = (unsigned char) (lane + 32 * k);
+		n += __popc(m);
+	}
+	return n;
 }
 
 /* launch for one pool slot: next shadow ray, or shade and bounce */
@@ -369,7 +375,7 @@ __device__ __forceinline__ void wf_launch_slot(const WfPool &pool, int s, const 
 }
 
 #ifndef RT_WAVEFRONT_MIN_BLOCKS
-#define RT_WAVEFRONT_MIN_BLOCKS 6
+#define RT_WAVEFRONT_MIN_BLOCKS 5
 #endif
 
 template <bool LBVH>
@@ -390,20 +396,28 @@ render_wavefront_kernel(const __grid_constant__ RtRenderParams P)
 
 	const unsigned total = (unsigned) (P.tiles_x * P.tiles_y) * 32u;
 	const bool lit = P.scene.light_index >= 0;
-	const int s0 = lane, s1 = lane + 32;
 	unsigned rays = 0;
 	bool exhausted = false;          /* warp-uniform */
 
-	pool.u(WF_STATE, s0) = 0u;
-	pool.u(WF_STATE, s1) = 0u;
+#pragma unroll
+	for (int k = 0; k < WF_SLOTS; k++) pool.u(WF_STATE, lane + 32 * k) = 0u;
 	__syncwarp();
 
 	for (;;) {
 		/* ---- lists of this round: slots with a pending ray (0) and idle slots (1) ---- */
-		unsigned st0 = pool.u(WF_STATE, s0), st1 = pool.u(WF_STATE, s1);
-		int n_trace = wf_list(WF_MODE(st0) == MODE_TRACE, WF_MODE(st1) == MODE_TRACE, list0);
-		int n_idle = wf_list(WF_MODE(st0) == MODE_IDLE, WF_MODE(st1) == MODE_IDLE, list1);
-		bool launching = __any_sync(full, WF_MODE(st0) == MODE_LAUNCH || WF_MODE(st1) == MODE_LAUNCH);
+		unsigned st[WF_SLOTS];
+		bool pa[WF_SLOTS], pb[WF_SLOTS];
+		bool mine_launching = false;
+#pragma unroll
+		for (int k = 0; k < WF_SLOTS; k++) {
+			st[k] = pool.u(WF_STATE, lane + 32 * k);
+			pa[k] = WF_MODE(st[k]) == MODE_TRACE;
+			pb[k] = WF_MODE(st[k]) == MODE_IDLE;
+			mine_launching = mine_launching || WF_MODE(st[k]) == MODE_LAUNCH;
+		}
+		int n_trace = wf_list(pa, list0);
+		int n_idle = wf_list(pb, list1);
+		bool launching = __any_sync(full, mine_launching);
 		unsigned base = 0;
 		if (!exhausted && n_idle > 0) {
 			if (lane == 0) base = atomicAdd(P.work_counter, (unsigned) n_idle);
@@ -503,9 +517,12 @@ render_wavefront_kernel(const __grid_constant__ RtRenderParams P)
 		__syncwarp();
 
 		/* ---- after the trace: fresh surfaces get their three tests first ... ---- */
-		st0 = pool.u(WF_STATE, s0); st1 = pool.u(WF_STATE, s1);
-		int n_fresh = wf_list((st0 & WF_FRESH) != 0 && WF_MODE(st0) == MODE_LAUNCH,
-		                      (st1 & WF_FRESH) != 0 && WF_MODE(st1) == MODE_LAUNCH, list0);
+#pragma unroll
+		for (int k = 0; k < WF_SLOTS; k++) {
+			st[k] = pool.u(WF_STATE, lane + 32 * k);
+			pa[k] = (st[k] & WF_FRESH) != 0 && WF_MODE(st[k]) == MODE_LAUNCH;
+		}
+		int n_fresh = wf_list(pa, list0);
 		__syncwarp();
 		for (int t = lane; t < 3 * n_fresh; t += 32) {
 			int j = (t * 171) >> 9;                         /* t / 3 for t < 256 */
@@ -517,14 +534,21 @@ render_wavefront_kernel(const __grid_constant__ RtRenderParams P)
 		}
 		__syncwarp();
 
-		/* ---- ... then one launch list, shadow rays first, shading last, so that the
-		 * chunks of 32 are homogeneous except at the single boundary ---- */
-		st0 = pool.u(WF_STATE, s0); st1 = pool.u(WF_STATE, s1);
-		const bool l0 = WF_MODE(st0) == MODE_LAUNCH, l1 = WF_MODE(st1) == MODE_LAUNCH;
-		int n_shadow = wf_list(l0 && WF_PENDING(st0) != 0, l1 && WF_PENDING(st1) != 0, list1);
-		int n_shade = wf_list(l0 && WF_PENDING(st0) == 0, l1 && WF_PENDING(st1) == 0, list1 + n_shadow);
+		/* ---- ... then one launch list: shadow rays first, shading from the next
+		 * multiple of 32, so that every chunk of 32 is homogeneous ---- */
+#pragma unroll
+		for (int k = 0; k < WF_SLOTS; k++) {
+			st[k] = pool.u(WF_STATE, lane + 32 * k);
+			bool l = WF_MODE(st[k]) == MODE_LAUNCH;
+			pa[k] = l && WF_PENDING(st[k]) != 0;
+			pb[k] = l && WF_PENDING(st[k]) == 0;
+		}
+		int n_shadow = wf_list(pa, list1);
+		int shade_at = (n_shadow + 31) & ~31;
+		int n_shade = wf_list(pb, list1 + shade_at);
 		__syncwarp();
-		for (int i = lane; i < n_shadow + n_shade; i += 32) wf_launch_slot(pool, list1[i], P.scene);
+		for (int i = lane; i < shade_at + n_shade; i += 32)
+			if (i < n_shadow || i >= shade_at) wf_launch_slot(pool, list1[i], P.scene);
 		__syncwarp();
 	}
 	count_rays(P, rays);
