@@ -202,8 +202,10 @@ render_pixel_kernel(const __grid_constant__ RtRenderParams P)
 #define RT_PERSISTENT_MIN_BLOCKS 6   /* 80 registers, 24 warps/SM: best of 5/6/8 on 4K scene_0 (2.39 / 2.37 / 2.51 ms) */
 #endif
 
+/* the LBVH walk is bound by node-fetch latency (ncu: long-scoreboard stalls), so
+ * it trades registers for resident warps: 8 CTAs/SM (64 registers) */
 template <bool LBVH>
-__global__ void __launch_bounds__(RT_BLOCK_THREADS, RT_PERSISTENT_MIN_BLOCKS)
+__global__ void __launch_bounds__(RT_BLOCK_THREADS, LBVH ? 8 : RT_PERSISTENT_MIN_BLOCKS)
 render_persistent_kernel(const __grid_constant__ RtRenderParams P)
 {
 	extern __shared__ __align__(16) unsigned char smem[];
