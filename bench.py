@@ -322,9 +322,20 @@ def main_gpu(args):
 
     # ---- end to end through the C ABI with a host framebuffer --------------
     # (rank 0 owns the host frame; with N>1 the bands are gathered to GPU 0 first)
-    host_frames = [torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True) for _ in range(2)] if rank == 0 else None
-    host_frame = host_frames[0] if rank == 0 else None
+    host_frames = [torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True) for _ in range(2)] if world == 1 else None
     e2e_opts = dict(scale=1, pass_index=0, variant=variant, kernel=kernel, stream=stream)
+    shared_host = None
+    if world > 1:
+        # one host frame shared by all ranks (POSIX shared memory, page-locked in every process):
+        # each rank copies the row blocks it rendered over its own PCIe link, no gather through GPU 0
+        shm_path = f"/dev/shm/rt_bench_frame_{os.environ.get('MASTER_PORT', '0')}"
+        if rank == 0:
+            np.lib.format.open_memmap(shm_path, mode="w+", dtype=np.float32, shape=(H, W, 3)).flush()
+        dist.barrier()
+        shared_host = np.load(shm_path, mmap_mode="r+")
+        host_addr = shared_host.ctypes.data
+        err = torch.cuda.cudart().cudaHostRegister(host_addr, shared_host.nbytes, 0)
+        assert int(err) == 0, f"cudaHostRegister failed: {err}"
 
     def step_e2e(i, pipeline):
         if world == 1:
@@ -332,13 +343,8 @@ def main_gpu(args):
             # pipeline=1: the call returns once the copy is queued; frame i+1 renders while frame i drains
             r.render_into(cam, host_frames[i & 1].data_ptr(), W, H, host=True, pipeline=int(pipeline), **e2e_opts)
         else:
-            full = step_device()
-            if rank == 0:
-                if p2p:
-                    r.copy_to_host(host_frame.data_ptr(), shared_ptr, W * H * 12, stream)
-                else:
-                    host_frame.copy_(full, non_blocking=True)
-                    torch.cuda.current_stream().synchronize()
+            r.render_into(cam, host_addr, W, H, host=True, interleave_count=world, interleave_index=rank, **e2e_opts)
+            dist.barrier()          # the frame is whole once every rank's copy has landed
 
     def run_e2e(n, pipeline):
         for i in range(3):
@@ -400,9 +406,9 @@ def main_gpu(args):
                 "h2d_bytes_per_step": 4096,            # RtRenderParams kernel-argument block (camera frame, views, sizes)
                 "d2h_bytes_per_step": W * H * 12,
                 "frames_per_s": e2e_steps / e2e_s, "steps": e2e_steps,
-                "mode": "pipelined: call k+1 renders while the copy stream drains frame k into the other pinned host frame; timed until rt_cuda_synchronize()" if world == 1 else "synchronous per step",
+                "mode": "pipelined: call k+1 renders while the copy stream drains frame k into the other pinned host frame; timed until rt_cuda_synchronize()" if world == 1 else "every rank renders its row blocks and copies them over its own PCIe link into one page-locked host frame shared by the ranks (POSIX shm); barrier per step",
                 "sync_value": rays_per_step * e2e_steps / e2e_sync_s / 1e6,
-                "api": "render_frame_cuda_ex(cam, host Vector3 frame, w, h, opts) [N>1: band render + composite on GPU 0 + D2H on rank 0]",
+                "api": "render_frame_cuda_ex(cam, host Vector3 frame, w, h, opts)",
             },
             "gpu_launches": args.steps * world,        # one render kernel per rank per step (NCCL kernels not counted)
             "clocks": clocks,
@@ -429,6 +435,14 @@ def main_gpu(args):
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
+        torch.cuda.cudart().cudaHostUnregister(host_addr)
+        del shared_host
+        dist.barrier()
+        if rank == 0:
+            try:
+                os.unlink(shm_path)
+            except OSError:
+                pass
     if p2p:
         torch.cuda.synchronize()
         if rank != 0:

@@ -467,7 +467,7 @@ static int interleave_shift(int scale)
  * GPU (8-GPU 4K frame: 1.09 ms kernel vs 0.40 ms on local memory), so remote
  * GPUs render locally and ship their blocks as one strided 2D copy. */
 static int copy_owned_blocks(void *dst, const void *src, const PassPlan &pl, int fb_row_offset, int il_n, int il_i,
-                             size_t bpp, cudaStream_t stream)
+                             size_t bpp, cudaStream_t stream, cudaMemcpyKind kind = cudaMemcpyDeviceToDevice)
 {
 	int rows_per_block = (1 << interleave_shift(pl.scale)) * pl.scale;
 	int band = pl.row1 - pl.row0;
@@ -483,11 +483,10 @@ static int copy_owned_blocks(void *dst, const void *src, const PassPlan &pl, int
 	size_t base = (size_t) (pl.row0 - fb_row_offset) * row_bytes + (size_t) il_i * chunk;
 	if (full > 0)
 		CU(cudaMemcpy2DAsync((char *) dst + base, (size_t) il_n * chunk, (const char *) src + base, (size_t) il_n * chunk,
-		                     chunk, (size_t) full, cudaMemcpyDeviceToDevice, stream));
+		                     chunk, (size_t) full, kind, stream));
 	if (own_partial_last) {
 		size_t off = (size_t) (pl.row0 - fb_row_offset) * row_bytes + (size_t) last * chunk;
-		CU(cudaMemcpyAsync((char *) dst + off, (const char *) src + off, (size_t) last_rows * row_bytes,
-		                   cudaMemcpyDeviceToDevice, stream));
+		CU(cudaMemcpyAsync((char *) dst + off, (const char *) src + off, (size_t) last_rows * row_bytes, kind, stream));
 	}
 	return RT_OK;
 }
@@ -767,7 +766,12 @@ static int render_pass(const RtCamera *cam, void *fb, int w, int h, const RtRend
 	if (!dev_fb) {
 		cudaStream_t st = use_user_stream ? (cudaStream_t) o->stream : d0.stream;
 		CU(cudaEventRecord(d0.ev[2], st));
-		CU(cudaMemcpyAsync(fb, d0.fb, fb_rows * (size_t) w * bpp, cudaMemcpyDeviceToHost, st));
+		if (o->interleave_count > 1) {
+			/* one-GPU-per-process ranks sharing a HOST frame: every rank copies only the
+			 * row blocks it rendered, over its own PCIe link, straight into the frame */
+			if ((rc = copy_owned_blocks(fb, d0.fb, pl, fb_row_offset, il_n, il_base, bpp, st, cudaMemcpyDeviceToHost)) != RT_OK) return rc;
+		} else
+			CU(cudaMemcpyAsync(fb, d0.fb, fb_rows * (size_t) w * bpp, cudaMemcpyDeviceToHost, st));
 		CU(cudaEventRecord(d0.ev[3], st));
 		CU(cudaStreamSynchronize(st));
 		if (stats) CU(cudaEventElapsedTime(&copy_ms, d0.ev[2], d0.ev[3]));

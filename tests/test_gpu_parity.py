@@ -393,6 +393,21 @@ def test_interleaved_row_blocks_equal_full_frame(renderer, small_sky, builtin_ob
         assert rays == st["rays"]
 
 
+def test_interleaved_blocks_into_shared_host_frame(renderer, small_sky, builtin_objects):
+    """Host destination + interleave: each rank copies only the row blocks it
+    rendered into the (shared) host frame; untouched rows stay as they were."""
+    renderer.upload_skybox(small_sky)
+    renderer.upload_scene(builtin_objects[0])
+    W, H = 320, 200
+    full, st = renderer.render_frame(Camera(), W, H, 1)
+    frame = np.full((H, W, 3), -1.0, np.float32)
+    for rank in range(3):
+        renderer.render_into(Camera(), frame.ctypes.data, W, H, host=True, scale=1, interleave_count=3, interleave_index=rank)
+        owned = np.array([(y // 16) % 3 <= rank for y in range(H)])
+        assert (frame[~owned] == -1.0).all() and (frame[owned] != -1.0).any()
+    assert np.array_equal(bits(frame), bits(full))
+
+
 def test_4k_properties(renderer, port, real_sky, builtin_objects):
     """BASELINE.json config 3 size (3840x2160): too large for the oracle to be
     quick, so use size-independent properties -- determinism, kernel
