@@ -343,8 +343,9 @@ def main_gpu(args):
             # pipeline=1: the call returns once the copy is queued; frame i+1 renders while frame i drains
             r.render_into(cam, host_frames[i & 1].data_ptr(), W, H, host=True, pipeline=int(pipeline), **e2e_opts)
         else:
-            r.render_into(cam, host_addr, W, H, host=True, interleave_count=world, interleave_index=rank, **e2e_opts)
-            dist.barrier()          # the frame is whole once every rank's copy has landed
+            r.render_into(cam, host_addr, W, H, host=True, pipeline=int(pipeline), interleave_count=world, interleave_index=rank, **e2e_opts)
+            if not pipeline:
+                dist.barrier()      # the frame is whole once every rank's copy has landed
 
     def run_e2e(n, pipeline):
         for i in range(3):
@@ -363,7 +364,7 @@ def main_gpu(args):
 
     e2e_steps = max(3, min(args.steps, 20))
     e2e_sync_s = run_e2e(e2e_steps, False)
-    e2e_s = run_e2e(e2e_steps, True) if world == 1 else e2e_sync_s
+    e2e_s = run_e2e(e2e_steps, True)
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
@@ -406,7 +407,7 @@ def main_gpu(args):
                 "h2d_bytes_per_step": 4096,            # RtRenderParams kernel-argument block (camera frame, views, sizes)
                 "d2h_bytes_per_step": W * H * 12,
                 "frames_per_s": e2e_steps / e2e_s, "steps": e2e_steps,
-                "mode": "pipelined: call k+1 renders while the copy stream drains frame k into the other pinned host frame; timed until rt_cuda_synchronize()" if world == 1 else "every rank renders its row blocks and copies them over its own PCIe link into one page-locked host frame shared by the ranks (POSIX shm); barrier per step",
+                "mode": "pipelined: call k+1 renders while the copy stream drains frame k into the other pinned host frame; timed until rt_cuda_synchronize()" if world == 1 else "pipelined like N=1; every rank renders its row blocks and copies them over its own PCIe link into one page-locked host frame shared by the ranks (POSIX shm); sync_value = with a barrier after every frame",
                 "sync_value": rays_per_step * e2e_steps / e2e_sync_s / 1e6,
                 "api": "render_frame_cuda_ex(cam, host Vector3 frame, w, h, opts)",
             },

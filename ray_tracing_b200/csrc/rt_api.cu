@@ -631,7 +631,7 @@ static int render_pass(const RtCamera *cam, void *fb, int w, int h, const RtRend
 	 * two staging buffers and copied to `fb` by the copy stream while the next
 	 * call already renders into the other one; the call returns without waiting.
 	 * `fb` is valid after rt_cuda_synchronize() (or once two later calls returned). */
-	bool pipelined = !dev_fb && o->pipeline && g.ngpu == 1 && !stats && o->interleave_count <= 1;
+	bool pipelined = !dev_fb && o->pipeline && g.ngpu == 1 && !stats;
 	int slot = 0;
 	if (pipelined) {
 		size_t need = fb_rows * (size_t) w * bpp;
@@ -733,7 +733,11 @@ static int render_pass(const RtCamera *cam, void *fb, int w, int h, const RtRend
 		cudaStream_t st = use_user_stream ? (cudaStream_t) o->stream : d0.stream;
 		CU(cudaEventRecord(d0.stage_rendered[slot], st));
 		CU(cudaStreamWaitEvent(d0.copy_stream, d0.stage_rendered[slot], 0));
-		CU(cudaMemcpyAsync(fb, d0.stage[slot], fb_rows * (size_t) w * bpp, cudaMemcpyDeviceToHost, d0.copy_stream));
+		if (o->interleave_count > 1) {
+			if ((rc = copy_owned_blocks(fb, d0.stage[slot], pl, fb_row_offset, il_n, il_base, bpp, d0.copy_stream,
+			                            cudaMemcpyDeviceToHost)) != RT_OK) return rc;
+		} else
+			CU(cudaMemcpyAsync(fb, d0.stage[slot], fb_rows * (size_t) w * bpp, cudaMemcpyDeviceToHost, d0.copy_stream));
 		CU(cudaEventRecord(d0.stage_copied[slot], d0.copy_stream));
 		return RT_OK;
 	}
