@@ -404,7 +404,7 @@ def main_gpu(args):
             "frames_per_s": 1e3 / per_step_ms,
             "e2e": {
                 "value": rays_per_step * e2e_steps / e2e_s / 1e6, "unit": "Mrays/s",
-                "h2d_bytes_per_step": 4096,            # RtRenderParams kernel-argument block (camera frame, views, sizes)
+                "h2d_bytes_per_step": int(host.load_library().rt_cuda_param_bytes()) * world,   # kernel-argument block (camera frame, views, sizes) per rank; scene and skybox are resident
                 "d2h_bytes_per_step": W * H * 12,
                 "frames_per_s": e2e_steps / e2e_s, "steps": e2e_steps,
                 "mode": "pipelined: call k+1 renders while the copy stream drains frame k into the other pinned host frame; timed until rt_cuda_synchronize()" if world == 1 else "pipelined like N=1; every rank renders its row blocks and copies them over its own PCIe link into one page-locked host frame shared by the ranks (POSIX shm); sync_value = with a barrier after every frame",

@@ -256,6 +256,8 @@ uint64_t rt_pixel_key(float px, float py, uint64_t pass_index);
 /* Register-only FP32 issue-rate probe: TFLOP/s of FMA chains (fma=1) or of
  * MUL+ADD pairs (fma=0, the ceiling of the no-contraction exact build). */
 int rt_cuda_debug_fp32_peak(int fma, float *tflops_out);
+/* Bytes of kernel arguments (camera frame, views, sizes) sent host -> device per launch. */
+size_t rt_cuda_param_bytes(void);
 /* Test knob: tau^2 of the sign shortcut in the light-sample sweep (negative =
  * default 4e-12).  1e30 forces the literal path; frames must be identical. */
 int rt_cuda_debug_set_sweep_threshold(float tau2);

@@ -555,10 +555,10 @@ static int launch_band(DeviceCtx &d, const RtCamera *cam, const PassPlan &pl, co
 			static int wf_per_sm[2][2] = {{0, 0}, {0, 0}}, wf_n[2][2] = {{-1, -1}, {-1, -1}};
 			int &per_sm = wf_per_sm[pl.exact ? 0 : 1][pl.lbvh ? 1 : 0];
 			int &for_n = wf_n[pl.exact ? 0 : 1][pl.lbvh ? 1 : 0];
-			if (per_sm < 1 || for_n != P.scene.n) {
+			if (per_sm < 1 || for_n != P.scene.n * 4096 + P.scene.num_runs) {
 				CU((pl.exact ? rt_exact_wavefront_blocks_per_sm : rt_fast_wavefront_blocks_per_sm)(&P, pl.lbvh, &per_sm));
 				if (per_sm < 1) return fail(RT_ERR_ARG, "the wavefront kernel does not fit: %d objects staged next to the path pool", P.scene.n);
-				for_n = P.scene.n;
+				for_n = P.scene.n * 4096 + P.scene.num_runs;
 			}
 			unsigned paths = (unsigned) rt_exact_wavefront_paths_per_block();
 			unsigned pixels = (unsigned) P.tiles_x * P.tiles_y * 32u;
@@ -572,10 +572,10 @@ static int launch_band(DeviceCtx &d, const RtCamera *cam, const PassPlan &pl, co
 			static int cached_per_sm[2][2] = {{0, 0}, {0, 0}}, cached_n[2][2] = {{-1, -1}, {-1, -1}};
 			int &per_sm = cached_per_sm[pl.exact ? 0 : 1][pl.lbvh ? 1 : 0];
 			int &for_n = cached_n[pl.exact ? 0 : 1][pl.lbvh ? 1 : 0];
-			if (per_sm < 1 || for_n != P.scene.n) {
+			if (per_sm < 1 || for_n != P.scene.n * 4096 + P.scene.num_runs) {
 				CU((pl.exact ? rt_exact_persistent_blocks_per_sm : rt_fast_persistent_blocks_per_sm)(&P, pl.lbvh, &per_sm));
 				if (per_sm < 1) per_sm = 1;
-				for_n = P.scene.n;
+				for_n = P.scene.n * 4096 + P.scene.num_runs;
 			}
 			unsigned warps_needed = (unsigned) P.tiles_x * P.tiles_y;
 			unsigned blocks_needed = (warps_needed + (RT_BLOCK_THREADS / 32) - 1) / (RT_BLOCK_THREADS / 32);
@@ -1122,3 +1122,6 @@ extern "C" int rt_cuda_debug_set_sweep_threshold(float tau2)
 	g.sweep_tau2 = tau2 >= 0.0f ? tau2 : 4e-12f;
 	return RT_OK;
 }
+
+/* size of the kernel-argument block that goes host -> device with every launch */
+extern "C" size_t rt_cuda_param_bytes(void) { return sizeof(RtRenderParams); }

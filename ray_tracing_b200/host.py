@@ -142,6 +142,7 @@ EXPORTED_SYMBOLS = [
     "rt_cuda_debug_fp32_peak",
     "rt_cuda_debug_div_check",
     "rt_cuda_debug_set_sweep_threshold",
+    "rt_cuda_param_bytes",
     "rt_cuda_shared_frame_create",
     "rt_cuda_shared_frame_open",
     "rt_cuda_shared_frame_close",
@@ -204,6 +205,7 @@ def load_library() -> C.CDLL:
     L.rt_cuda_shared_frame_close.argtypes = [C.c_void_p, C.c_int]
     L.rt_cuda_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.rt_cuda_debug_set_sweep_threshold.argtypes = [C.c_float]
+    L.rt_cuda_param_bytes.restype = C.c_size_t
     L.rt_pixel_key.restype = C.c_uint64
     L.rt_pixel_key.argtypes = [C.c_float, C.c_float, C.c_uint64]
     _lib = L
