@@ -40,7 +40,7 @@ $(OBJ)/rt_render_exact.o: $(SRC)/rt_render.cu $(DEVICE_HDRS)
 	    2> $(OBJ)/rt_render_exact.ptxas.log || (cat $(OBJ)/rt_render_exact.ptxas.log; false)
 $(OBJ)/rt_render_fast.o: $(SRC)/rt_render.cu $(DEVICE_HDRS)
 	@mkdir -p $(OBJ)
-	$(NVCC) $(NVFLAGS) -DRT_NS=rt_fast -fmad=true -c -o $@ $< \
+	$(NVCC) $(NVFLAGS) -DRT_NS=rt_fast -DRT_FAST_MATH=1 -fmad=true -c -o $@ $< \
 	    2> $(OBJ)/rt_render_fast.ptxas.log || (cat $(OBJ)/rt_render_fast.ptxas.log; false)
 
 $(LIB): $(HOST_OBJS) $(CUDA_OBJS)

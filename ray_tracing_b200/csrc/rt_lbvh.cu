@@ -47,6 +47,9 @@ static int lfail(int code, const char *fmt, ...)
 	} while (0)
 
 #define RT_FUZZ_K 32.0
+static double g_fuzz_k = RT_FUZZ_K;
+static double g_slack = 1e-3;
+extern "C" void rt_lbvh_debug_set(double k, double slack) { g_fuzz_k = k; g_slack = slack; }
 
 /* ---- Morton keys -------------------------------------------------------- */
 
@@ -234,7 +237,7 @@ int rt_lbvh_refit(RtLbvh *bvh, const float4 *geomA, const float4 *geomB, float d
 	int n = bvh->num_prims;
 	if (n <= 0) return RT_OK;
 	double D = (double) d_max;
-	double fuzz_r2 = RT_FUZZ_K * ldexp(1.0, -24) * D * D;
+	double fuzz_r2 = g_fuzz_k * ldexp(1.0, -24) * D * D;
 	double mag = fmax(fmax(fabs((double) bvh->lo.x), fabs((double) bvh->hi.x)),
 	                  fmax(fmax(fabs((double) bvh->lo.y), fabs((double) bvh->hi.y)),
 	                       fmax(fabs((double) bvh->lo.z), fabs((double) bvh->hi.z))));
@@ -254,7 +257,7 @@ int rt_lbvh_refit(RtLbvh *bvh, const float4 *geomA, const float4 *geomB, float d
 		LCU(cudaStreamSynchronize(stream));
 	}
 	bvh->d_max = d_max;
-	bvh->t_slack = (float) (1e-3 * D);
+	bvh->t_slack = (float) (g_slack * D);
 	return RT_OK;
 }
 
