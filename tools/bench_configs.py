@@ -23,11 +23,13 @@ def main():
     ap.add_argument("--variant", default="exact")
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--skip-100k", action="store_true")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "pixel", "persistent", "wavefront"])
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     import torch
 
     variant = host.RT_VARIANT_FAST if a.variant == "fast" else host.RT_VARIANT_EXACT
+    kern = {"auto": 0, "pixel": 1, "persistent": 2, "wavefront": 3}[a.kernel]
     faces, sky_desc = bench.load_skybox_faces()
     r = host.Renderer(num_gpus=1)
     r.upload_skybox(faces)
@@ -38,7 +40,7 @@ def main():
         frame = torch.zeros((h, w, 3), dtype=torch.float32, device="cuda")
         best, st = 1e9, None
         for _ in range(a.reps):
-            st = r.render_into(cam, frame.data_ptr(), w, h, stats=True, variant=variant, **kw)
+            st = r.render_into(cam, frame.data_ptr(), w, h, stats=True, variant=variant, kernel=kern, **kw)
             best = min(best, st["render_ms"])
         rec = dict(config=label, w=w, h=h, ms=best, rays=st["rays"], mrays_s=st["rays"] / best / 1e3, fps=1e3 / best, **{k: v for k, v in kw.items() if k in ("scale", "traversal")})
         out.append(rec)
@@ -56,7 +58,7 @@ def main():
     best = 1e9
     for _ in range(a.reps):
         torch.cuda.synchronize(); t0 = time.perf_counter()
-        _, st = r.render_sweep(cam, 1920, 1080, 16, 0, ptr=frame.data_ptr(), stats=False, variant=variant)
+        _, st = r.render_sweep(cam, 1920, 1080, 16, 0, ptr=frame.data_ptr(), stats=False, variant=variant, kernel=kern)
         r.synchronize(); best = min(best, time.perf_counter() - t0)
     rec = dict(config="4: scene_0 1920x1080 sweep 16->1 (5 passes, accumulate+resolve)", ms=best * 1e3, sweeps_per_s=1 / best)
     out.append(rec); print(json.dumps(rec))
