@@ -239,6 +239,19 @@ int rt_cuda_shared_frame_open(const void *handle64, void **dev_ptr);
 int rt_cuda_shared_frame_close(void *dev_ptr, int owner);
 int rt_cuda_copy_to_host(void *host_dst, const void *dev_src, size_t bytes, void *stream);
 
+/* The reference's frame scheduler (main.c:324-482) in three calls:
+ *   rt_cuda_set_progressive(init_scale, num_columns)   the --init-scale / --threads flags
+ *   rt_cuda_invalidate_accumulation()                  invalidate_accumulation() (main.c:115-124):
+ *                                                      accum = 0, generation++, back to init_scale
+ *   rt_cuda_update_frame(cam, fb, w, h, budget_ms,...)  update_frame() (main.c:450-482): at least one
+ *       pass at the current scale (halving after each, main.c:402-403), then more passes while the
+ *       device time spent stays within budget_ms (0 = exactly one pass); fb = accum / count. */
+int      rt_cuda_set_progressive(int init_scale, int num_columns);
+int      rt_cuda_invalidate_accumulation(void);
+uint32_t rt_cuda_accum_generation(void);
+int      rt_cuda_update_frame(const RtCamera *cam, void *fb, int w, int h, double budget_ms,
+                              const RtRenderOpts *opts, RtRenderStats *stats);
+
 /* Block until all work issued by the library has finished. */
 int rt_cuda_synchronize(void);
 

@@ -1125,3 +1125,108 @@ extern "C" int rt_cuda_debug_set_sweep_threshold(float tau2)
 
 /* size of the kernel-argument block that goes host -> device with every launch */
 extern "C" size_t rt_cuda_param_bytes(void) { return sizeof(RtRenderParams); }
+
+/* ------------------------------------------------ interactive frame loop */
+
+/*
+ * The reference's frame scheduler in three calls: workers start
+ * at --init-scale and halve the scale after every published pass
+ * (main.c:354, 402-403); any camera/window change bumps the generation counter,
+ * zeroes accum and sends them back to init_scale (main.c:115-124, 405-408);
+ * update_frame() shows accum / count (main.c:450-482).
+ */
+static struct {
+	int      init_scale = 8;            /* main.c:589 default */
+	int      num_columns = 1;
+	int      scale = 8;
+	uint64_t pass = 0;
+	uint32_t generation = 0;            /* accum_generation, main.c:59 */
+} g_loop;
+
+extern "C" int rt_cuda_set_progressive(int init_scale, int num_columns)
+{
+	if (init_scale != 1 && init_scale != 2 && init_scale != 4 && init_scale != 8 && init_scale != 16)
+		return fail(RT_ERR_ARG, "init_scale must be a power of 2 between 1 and 16 (main.c:598)");
+	if (num_columns < 1) return fail(RT_ERR_ARG, "num_columns must be >= 1");
+	g_loop.init_scale = init_scale;
+	g_loop.num_columns = num_columns > 32 ? 32 : num_columns;          /* MAX_COLUMNS, main.c:632 */
+	g_loop.scale = init_scale;
+	return RT_OK;
+}
+
+extern "C" int rt_cuda_invalidate_accumulation(void)
+{
+	g_loop.scale = g_loop.init_scale;
+	g_loop.generation++;
+	return rt_cuda_accum_reset();
+}
+
+extern "C" uint32_t rt_cuda_accum_generation(void) { return g_loop.generation; }
+
+/* One update_frame(): at least one pass at the current scale, then further
+ * passes (scale halving down to 1, then more scale-1 samples) while the time
+ * already spent stays below budget_ms -- what the reference's free-running
+ * workers achieve between two redraws.  fb receives accum / count. */
+extern "C" int rt_cuda_update_frame(const RtCamera *cam, void *fb, int w, int h, double budget_ms,
+                                    const RtRenderOpts *opts, RtRenderStats *stats)
+{
+	int rc = require_ready();
+	if (rc != RT_OK) return rc;
+	RtRenderOpts o;
+	if (opts) o = *opts; else rt_render_opts_default(&o);
+	o.num_columns = g_loop.num_columns;
+	o.scale = g_loop.scale;
+	if ((rc = validate_common(cam, fb, w, h, &o)) != RT_OK) return rc;
+	bool dev_fb = o.fb_memory == RT_MEM_DEVICE || (o.fb_memory == RT_MEM_AUTO && is_device_pointer(fb));
+	RtRenderStats total;
+	memset(&total, 0, sizeof(total));
+	DeviceCtx &d0 = g.dev[0];
+	cudaEvent_t t0 = d0.ev[2], t1 = d0.ev[3];
+	if ((rc = select_device(d0)) != RT_OK) return rc;
+	cudaStream_t st0 = (g.ngpu == 1 && o.stream) ? (cudaStream_t) o.stream : d0.stream;
+	CU(cudaEventRecord(t0, st0));
+	for (int passes = 0;; passes++) {
+		o.scale = g_loop.scale;
+		o.pass_index = g_loop.pass++;
+		RtRenderStats st;
+		memset(&st, 0, sizeof(st));
+		/* decide after this pass whether another one fits: needs the elapsed device time */
+		RtRenderOpts oo = o;
+		void *dst = fb;
+		bool last_possible = budget_ms <= 0.0;
+		if (!dev_fb && !last_possible) {
+			/* keep intermediate passes on the device; the final one copies to the host */
+			size_t need = (size_t) w * h * bytes_per_pixel(o.fb_format);
+			if (d0.fb_bytes < need) {
+				CU(cudaFree(d0.fb));
+				d0.fb = nullptr; d0.fb_bytes = 0;
+				CU(cudaMalloc(&d0.fb, need));
+				d0.fb_bytes = need;
+			}
+			dst = d0.fb;
+			oo.fb_memory = RT_MEM_DEVICE;
+		}
+		rc = render_pass(cam, dst, w, h, &oo, true, &st, true);
+		if (rc != RT_OK) return rc;
+		total.rays += st.rays; total.pixels += st.pixels; total.render_ms += st.render_ms;
+		total.kernel_launches += st.kernel_launches;
+		if (g_loop.scale > 1) g_loop.scale >>= 1;                      /* main.c:402-403 */
+		if (last_possible) break;
+		if ((rc = select_device(d0)) != RT_OK) return rc;
+		CU(cudaEventRecord(t1, st0));
+		CU(cudaEventSynchronize(t1));
+		float ms = 0.0f;
+		CU(cudaEventElapsedTime(&ms, t0, t1));
+		/* another pass costs about what the last one did (x4 while the scale still halves) */
+		double next = st.render_ms * (o.scale > 1 ? 4.0 : 1.0);
+		if (ms + next > budget_ms) {
+			if (!dev_fb) {
+				CU(cudaMemcpyAsync(fb, d0.fb, (size_t) w * h * bytes_per_pixel(o.fb_format), cudaMemcpyDeviceToHost, st0));
+				CU(cudaStreamSynchronize(st0));
+			}
+			break;
+		}
+	}
+	if (stats) *stats = total;
+	return RT_OK;
+}

@@ -143,6 +143,10 @@ EXPORTED_SYMBOLS = [
     "rt_cuda_debug_div_check",
     "rt_cuda_debug_set_sweep_threshold",
     "rt_cuda_param_bytes",
+    "rt_cuda_set_progressive",
+    "rt_cuda_invalidate_accumulation",
+    "rt_cuda_accum_generation",
+    "rt_cuda_update_frame",
     "rt_cuda_shared_frame_create",
     "rt_cuda_shared_frame_open",
     "rt_cuda_shared_frame_close",
@@ -206,6 +210,9 @@ def load_library() -> C.CDLL:
     L.rt_cuda_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.rt_cuda_debug_set_sweep_threshold.argtypes = [C.c_float]
     L.rt_cuda_param_bytes.restype = C.c_size_t
+    L.rt_cuda_set_progressive.argtypes = [C.c_int, C.c_int]
+    L.rt_cuda_accum_generation.restype = C.c_uint32
+    L.rt_cuda_update_frame.argtypes = [C.POINTER(RtCamera), C.c_void_p, C.c_int, C.c_int, C.c_double, C.POINTER(RtRenderOpts), C.POINTER(RtRenderStats)]
     L.rt_pixel_key.restype = C.c_uint64
     L.rt_pixel_key.argtypes = [C.c_float, C.c_float, C.c_uint64]
     _lib = L
@@ -473,6 +480,26 @@ class Renderer:
 
     def copy_to_host(self, host_ptr: int, dev_ptr: int, nbytes: int, stream=None) -> None:
         _check(self.lib.rt_cuda_copy_to_host(C.c_void_p(host_ptr), C.c_void_p(dev_ptr), nbytes, C.c_void_p(stream) if stream else None))
+
+    # -- the reference's frame loop (main.c:324-482)
+    def set_progressive(self, init_scale: int, num_columns: int = 1) -> None:
+        _check(self.lib.rt_cuda_set_progressive(init_scale, num_columns))
+
+    def invalidate_accumulation(self) -> None:
+        _check(self.lib.rt_cuda_invalidate_accumulation())
+
+    def accum_generation(self) -> int:
+        return self.lib.rt_cuda_accum_generation()
+
+    def update_frame(self, camera: Camera, w: int, h: int, budget_ms: float = 0.0, *, out=None, **opts):
+        o = self._opts(**opts)
+        if out is None:
+            out = np.zeros((h, w, 3), np.float32) if o.fb_format == RT_FB_F32X3 else np.zeros((h, w, 4), np.uint8)
+        o.fb_memory = RT_MEM_HOST
+        st = RtRenderStats()
+        cam = camera.as_struct()
+        _check(self.lib.rt_cuda_update_frame(C.byref(cam), out.ctypes.data, w, h, budget_ms, C.byref(o), C.byref(st)))
+        return out, _stats_dict(st)
 
     def accum_reset(self) -> None:
         _check(self.lib.rt_cuda_accum_reset())

@@ -335,6 +335,45 @@ def test_progressive_sweep_vs_oracle(renderer, port, small_sky, builtin_objects)
     assert renderer.accum_count() == 0.0
 
 
+def test_update_frame_loop_matches_reference_scheduler(renderer, port, small_sky, builtin_objects):
+    """rt_cuda_update_frame / rt_cuda_invalidate_accumulation reproduce the
+    workers' schedule (main.c:354, 402-408): init_scale, halving per published
+    pass, restart after an invalidation; every frame is accum / count."""
+    W, H = 160, 96
+    renderer.upload_skybox(small_sky)
+    renderer.upload_scene(builtin_objects[0])
+    world = port.world(builtin_objects[0], small_sky)
+    renderer.set_progressive(8, 4)
+    renderer.invalidate_accumulation()
+    gen = renderer.accum_generation()
+    acc = np.zeros((H, W, 3), np.float32)
+    count = np.float32(0)
+    p = 0
+    frames = []
+    for s in (8, 4, 2, 1, 1):
+        frame, st = renderer.update_frame(Camera(), W, H, 0.0)
+        data, _ = port.render(world, W, H, s, 4, p)
+        p += 1
+        port.accumulate(acc, data, s)
+        count = np.float32(count + np.float32(1.0) / np.float32(s * s))
+        assert np.array_equal(bits(frame), bits(port.resolve(acc, count))), s
+    # camera moved: back to init_scale, accum cleared, generation bumped
+    renderer.invalidate_accumulation()
+    assert renderer.accum_generation() == gen + 1 and renderer.accum_count() == 0.0
+    cam = Camera((4.5, 4.5, 4.5), (-1, -1, -1), (0, 1, 0), 30.0)
+    frame, st = renderer.update_frame(cam, W, H, 0.0)
+    data, _ = port.render(port.world(builtin_objects[0], small_sky, cam.as_dict()), W, H, 8, 4, p)
+    acc = np.zeros((H, W, 3), np.float32)
+    port.accumulate(acc, data, 8)
+    assert np.array_equal(bits(frame), bits(port.resolve(acc, np.float32(1.0) / np.float32(64))))
+    # a time budget buys several passes in one call
+    renderer.invalidate_accumulation()
+    frame, st = renderer.update_frame(Camera(), W, H, 50.0)
+    assert renderer.accum_count() > 1.0 and st["kernel_launches"] >= 5
+    renderer.set_progressive(8, 1)
+    renderer.invalidate_accumulation()
+
+
 def test_sweep_1080p_vs_oracle(renderer, port, real_sky, builtin_objects):
     W, H = 1920, 1080
     renderer.upload_skybox(real_sky)
