@@ -133,6 +133,53 @@ __device__ __forceinline__ void store_cell(const RtRenderParams &P, const Cell &
 	}
 }
 
+/* One output pixel of a tile (shared by the per-lane and the warp-wide store). */
+__device__ __forceinline__ void store_pixel(const RtRenderParams &P, int x, int y, f3 color)
+{
+	f3 out = color;
+	if (P.accum) {
+		float *a = P.accum + 3 * ((size_t) (y - P.accum_row_offset) * P.W + x);
+		f3 acc = mk(a[0] + color.x * P.accum_weight, a[1] + color.y * P.accum_weight, a[2] + color.z * P.accum_weight);
+		a[0] = acc.x; a[1] = acc.y; a[2] = acc.z;
+		out = scl3(acc, P.inv_count);
+	}
+	size_t p = (size_t) (y - P.fb_row_offset) * P.W + x;
+	if (P.fb_format == RT_FB_F32X3) {
+		float *f = reinterpret_cast<float *>(P.fb) + 3 * p;
+		f[0] = out.x; f[1] = out.y; f[2] = out.z;
+	} else {
+		uchar4 q;
+		q.x = (unsigned char) __float2uint_rz(out.x * 255.0f);
+		q.y = (unsigned char) __float2uint_rz(out.y * 255.0f);
+		q.z = (unsigned char) __float2uint_rz(out.z * 255.0f);
+		q.w = 255;
+		reinterpret_cast<uchar4 *>(P.fb)[p] = q;
+	}
+}
+
+/* Warp-wide tile replication for low-res passes (scale >= 4): the finished lanes'
+ * tiles are written one after the other by all 32 lanes, consecutive lanes on
+ * consecutive pixels of a tile row.  A single lane replicating a 16x16 tile does
+ * 256 dependent read-modify-writes (a scale-16 accumulate pass took 0.76 ms
+ * against 0.21 ms for the tracing itself).  All lanes must call. */
+__device__ __forceinline__ void store_cells_warp(const RtRenderParams &P, bool has, const Cell &c, f3 color)
+{
+	const unsigned full = 0xffffffffu;
+	const int lane = threadIdx.x & 31;
+	unsigned todo = __ballot_sync(full, has);
+	while (todo) {
+		int src = __ffs(todo) - 1;
+		todo &= todo - 1;
+		int x0 = __shfl_sync(full, c.x0, src), y0 = __shfl_sync(full, c.y0, src), tw = __shfl_sync(full, c.tw, src);
+		f3 col = mk(__shfl_sync(full, color.x, src), __shfl_sync(full, color.y, src), __shfl_sync(full, color.z, src));
+		int n = tw * P.scale;
+		for (int i = lane; i < n; i += 32) {
+			int g = i / tw, t = i - g * tw;
+			store_pixel(P, x0 + t, y0 + g, col);
+		}
+	}
+}
+
 __device__ __forceinline__ void count_rays(const RtRenderParams &P, unsigned rays)
 {
 	for (int o = 16; o > 0; o >>= 1) rays += __shfl_xor_sync(0xffffffffu, rays, o);
@@ -226,7 +273,10 @@ render_persistent_kernel(const __grid_constant__ RtRenderParams P)
 	for (;;) {
 		unsigned idle = __ballot_sync(full, p.mode == MODE_IDLE);
 		if (idle) {
-			if (p.mode == MODE_IDLE && owns) {
+			if (P.scale >= 4) {             /* warp-uniform */
+				store_cells_warp(P, p.mode == MODE_IDLE && owns, c, path_final(p));
+				if (p.mode == MODE_IDLE) owns = false;
+			} else if (p.mode == MODE_IDLE && owns) {
 				store_cell(P, c, path_final(p));
 				owns = false;
 			}
