@@ -325,6 +325,10 @@ def test_progressive_sweep_vs_oracle(renderer, port, small_sky, builtin_objects)
     assert np.array_equal(bits(frame), bits(want))
     assert st["rays"] == rays
     assert renderer.accum_count() == count
+    for kern in (RT_KERNEL_PIXEL, RT_KERNEL_WAVEFRONT):
+        other, so = renderer.render_sweep(Camera(), W, H, 16, first_pass=0, kernel=kern)
+        assert np.array_equal(bits(other), bits(want)) and so["rays"] == rays
+    frame, st = renderer.render_sweep(Camera(), W, H, 16, first_pass=0)
     # continuing at scale 1 keeps averaging (workers stay at scale 1, main.c:402)
     frame2, _ = renderer.render_frame(Camera(), W, H, 1, pass_index=5, accumulate=1)
     data, _ = port.render(world, W, H, 1, 1, 5)
@@ -430,6 +434,15 @@ def test_interleaved_row_blocks_equal_full_frame(renderer, small_sky, builtin_ob
             rays += bst["rays"]
         assert np.array_equal(bits(frame.cpu().numpy()), bits(full)), (W, H, s, world)
         assert rays == st["rays"]
+    # same split with the 8-bit framebuffer (4 B/px) and a remote-style staged copy
+    W, H, s, world = 320, 200, 1, 3
+    full8, _ = renderer.render_frame(Camera(), W, H, s, fb_format=RT_FB_U8X4)
+    frame8 = torch.zeros((H, W, 4), dtype=torch.uint8, device="cuda")
+    for rank in range(world):
+        renderer.render_into(Camera(), frame8.data_ptr(), W, H, scale=s, fb_format=RT_FB_U8X4,
+                             interleave_count=world, interleave_index=rank, remote_fb=int(rank != 0))
+    renderer.synchronize()
+    assert np.array_equal(frame8.cpu().numpy(), full8)
 
 
 def test_interleaved_blocks_into_shared_host_frame(renderer, small_sky, builtin_objects):
