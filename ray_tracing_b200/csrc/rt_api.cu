@@ -782,8 +782,6 @@ static int render_pass(const RtCamera *cam, void *fb, int w, int h, const RtRend
 	}
 	if (stats) {
 		stats->rays = rays;
-		int lw = w / pl.scale;
-		(void) lw;
 		int colw = w / pl.ncols;
 		int cells_per_row = pl.ncols * ((colw + pl.scale - 1) / pl.scale);
 		int lh = h / pl.scale;
@@ -1117,8 +1115,6 @@ extern "C" int rt_cuda_copy_to_host(void *host_dst, const void *dev_src, size_t 
  * normalise-then-dot path for every sample; results must not change. */
 extern "C" int rt_cuda_debug_set_sweep_threshold(float tau2)
 {
-	float keep = g.sweep_tau2;
-	(void) keep;
 	g.sweep_tau2 = tau2 >= 0.0f ? tau2 : 4e-12f;
 	return RT_OK;
 }

@@ -1,19 +1,21 @@
 /*
  * rt_render.cu -- the render kernels (sm_100a).  Compiled twice, see
- * rt_device.cuh: -DRT_NS=rt_exact -fmad=false and -DRT_NS=rt_fast -fmad=true.
+ * rt_device.cuh: -DRT_NS=rt_exact -fmad=false and -DRT_NS=rt_fast -fmad=true -DRT_FAST_MATH.
  *
  * Replaces: worker()/render_column()/pixel() (src/main.c:131-414) -- the
  * pthread-per-column pool becomes one launch over low-res pixels.
  *
- * Two kernels, same device functions:
+ * Three kernels, same device functions, bit-identical frames:
  *   render_pixel_kernel       one thread per low-res pixel, 8x4 pixel tile per
- *                             warp, each thread runs its whole path;
- *   render_persistent_kernel  resident warps; a lane whose path ended stores
- *                             its pixel and immediately starts the next pixel
- *                             of the warp's batch, so the convergent
+ *                             warp, each thread runs its whole path (baseline);
+ *   render_persistent_kernel  (default) resident warps; a lane whose path ended
+ *                             stores its pixel and immediately starts the next
+ *                             pixel of the warp's batch, so the convergent
  *                             nearest-hit scan keeps all 32 lanes busy while
  *                             paths are 1..40 rays long (SURVEY.md 8(a)
- *                             divergence data).
+ *                             divergence data);
+ *   render_wavefront_kernel   per-warp pools of 64 paths in shared memory, every
+ *                             phase over a compacted list of the paths needing it.
  * Scenes up to RT_SMEM_MAX_OBJECTS are scanned linearly from shared memory
  * (every lane reads the same primitive: broadcast, no bank conflicts); larger
  * ones walk the LBVH in global memory.
