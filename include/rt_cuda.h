@@ -134,6 +134,9 @@ RtCamera  rt_camera_snapshot(void);
 
 /* main.c:666-670 quantisation rule: (uint8_t)(x*255), row order unchanged. */
 void rt_quantize_frame(const float *frame_rgb, size_t num_pixels, uint8_t *out_rgb);
+/* screenshot() (main.c:637-681) without the file-name search: quantise, flip vertically, write an
+ * 8-bit RGB PNG (or a binary PPM when the path ends in ".ppm"). */
+int  rt_save_screenshot(const char *path, const float *frame_rgb, int w, int h);
 
 /* ------------------------------------------------------------------------- */
 /* Device lifecycle                                                          */

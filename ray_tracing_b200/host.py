@@ -119,6 +119,7 @@ EXPORTED_SYMBOLS = [
     "rt_get_camera_pos",
     "rt_camera_snapshot",
     "rt_quantize_frame",
+    "rt_save_screenshot",
     "rt_cuda_init",
     "rt_cuda_init_device",
     "rt_cuda_shutdown",
@@ -185,6 +186,7 @@ def load_library() -> C.CDLL:
     L.rt_camera_snapshot.restype = RtCamera
     L.rt_quantize_frame.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
     L.rt_quantize_frame.restype = None
+    L.rt_save_screenshot.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int]
     L.rt_cuda_init.argtypes = [C.c_int]
     L.rt_cuda_init_device.argtypes = [C.c_int]
     L.rt_cuda_shutdown.restype = None
@@ -347,6 +349,12 @@ def quantize_frame(frame: np.ndarray) -> np.ndarray:
     out = np.empty(frame.shape, np.uint8)
     load_library().rt_quantize_frame(frame.ctypes.data, frame.size // 3, out.ctypes.data)
     return out
+
+
+def save_screenshot(path: str, frame: np.ndarray) -> None:
+    """screenshot() of main.c:637-681: quantise, flip, write PNG (or PPM)."""
+    frame = np.ascontiguousarray(frame, dtype=np.float32)
+    _check(load_library().rt_save_screenshot(os.fsencode(path), frame.ctypes.data, frame.shape[1], frame.shape[0]))
 
 
 def pixel_key(px: float, py: float, pass_index: int = 0) -> int:

@@ -54,3 +54,26 @@ def test_quantize_rule():
     want = (x * np.float32(255)).astype(np.uint8)   # truncation
     assert np.array_equal(q, want)
     assert q[0].tolist() == [0, 127, 255]
+
+
+def test_save_screenshot_png_and_ppm(tmp_path):
+    """screenshot() pixel path (main.c:637-681): quantise, flip vertically, PNG."""
+    rng = np.random.default_rng(3)
+    frame = rng.uniform(0, 1, (37, 53, 3)).astype(np.float32)
+    frame[0, 0] = (1.0, 0.0, 0.5)
+    want = host.quantize_frame(frame)[::-1]
+    host.save_screenshot(str(tmp_path / "s.ppm"), frame)
+    with open(tmp_path / "s.ppm", "rb") as f:
+        assert f.readline() == b"P6\n" and f.readline() == b"53 37\n" and f.readline() == b"255\n"
+        assert np.array_equal(np.frombuffer(f.read(), np.uint8).reshape(37, 53, 3), want)
+    host.save_screenshot(str(tmp_path / "s.png"), frame)
+    try:
+        from PIL import Image
+    except ImportError:
+        return
+    im = Image.open(tmp_path / "s.png")
+    assert im.size == (53, 37) and im.mode == "RGB"
+    assert np.array_equal(np.asarray(im), want)
+    big = rng.uniform(0, 1, (300, 400, 3)).astype(np.float32)      # several stored deflate blocks
+    host.save_screenshot(str(tmp_path / "b.png"), big)
+    assert np.array_equal(np.asarray(Image.open(tmp_path / "b.png")), host.quantize_frame(big)[::-1])

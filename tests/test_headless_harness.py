@@ -55,7 +55,7 @@ def test_harness_progressive_frames_match_oracle(tmp_path, port, real_sky):
     assert np.array_equal(bits(got), bits(want))
     assert abs(info["accum_count"] - float(count)) < 1e-3      # printed with 4 decimals
 
-    # screenshot rule: (uint8_t)(x*255), flipped vertically, P6
+    # screenshot rule: (uint8_t)(x*255), flipped vertically, P6 (PNG covered in test_camera_host.py)
     with open(ppm, "rb") as f:
         assert f.readline() == b"P6\n" and f.readline() == f"{W} {H}\n".encode() and f.readline() == b"255\n"
         px = np.frombuffer(f.read(), np.uint8).reshape(H, W, 3)

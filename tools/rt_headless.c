@@ -13,7 +13,7 @@
  * pass (main.c:402-403).  --keys replays W/A/S/D presses (main.c:536-558): each
  * moves the camera by 0.5 and invalidates the accumulation.  --dump writes what
  * screenshot() would (main.c:637-681): (uint8_t)(x*255), flipped vertically,
- * as a binary PPM.
+ * as a PNG (binary PPM if the name ends in .ppm).
  *
  * The skybox JPEGs are decoded by stb_image when this file is compiled with
  * -DRT_HAVE_STB -I<dir containing stb/stb_image.h> (the reference vendors it
@@ -175,18 +175,11 @@ int main(int argc, char **argv)
 		if (fp) fclose(fp);
 	}
 	if (dump) {
-		/* screenshot(): quantise, flip vertically (stbi_flip_vertically_on_write(1)) */
-		uint8_t *q = (uint8_t *) malloc((size_t) w * h * 3);
-		rt_quantize_frame((const float *) frame, (size_t) w * h, q);
-		FILE *fp = fopen(dump, "wb");
-		if (!fp) fprintf(stderr, "Couldn't take screenshot (%s)\n", dump);
-		else {
-			fprintf(fp, "P6\n%d %d\n255\n", w, h);
-			for (int y = h - 1; y >= 0; y--) fwrite(q + (size_t) y * w * 3, 1, (size_t) w * 3, fp);
-			fclose(fp);
+		/* screenshot(): quantise, flip vertically, PNG (or PPM by extension) */
+		if (rt_save_screenshot(dump, (const float *) frame, w, h) != RT_OK)
+			fprintf(stderr, "Could not take screenshot (write error)\n");
+		else
 			fprintf(stderr, "Took screenshot! (%s)\n", dump);
-		}
-		free(q);
 	}
 	rt_cuda_shutdown();
 	free(frame);
