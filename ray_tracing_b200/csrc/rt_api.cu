@@ -596,6 +596,8 @@ static int validate_common(const RtCamera *cam, void *fb, int w, int h, const Rt
 	if (!o || o->struct_size != sizeof(RtRenderOpts)) return fail(RT_ERR_ARG, "opts->struct_size mismatch (ABI)");
 	if (o->scale < 1) return fail(RT_ERR_ARG, "scale must be >= 1");
 	if (o->num_columns < 1 || o->num_columns > w) return fail(RT_ERR_ARG, "num_columns out of range");
+	if (w / o->scale < 2 || h / o->scale < 2)
+		return fail(RT_ERR_ARG, "frame %dx%d is too small for scale %d: u = i/(w/scale - 1), v = j/(h/scale - 1) divide by zero (main.c:293-294)", w, h, o->scale);
 	if (o->fb_format != RT_FB_F32X3 && o->fb_format != RT_FB_U8X4) return fail(RT_ERR_ARG, "unknown fb_format");
 	if (o->variant != RT_VARIANT_EXACT && o->variant != RT_VARIANT_FAST) return fail(RT_ERR_ARG, "unknown variant");
 	if (!g.have_scene) return fail(RT_ERR_STATE, "no scene uploaded (rt_cuda_upload_scene)");

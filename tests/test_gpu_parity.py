@@ -246,6 +246,8 @@ def test_edge_cases(renderer, port, small_sky):
         renderer.render_frame(Camera(), 64, 36, 0)
     with pytest.raises(host.RtError):
         renderer.render_frame(Camera(), 64, 36, 2, rows=(3, 20))
+    with pytest.raises(host.RtError):      # H/scale == 1: the reference's v = j/(lh-1) divides by zero
+        renderer.render_frame(Camera(), 95, 13, 8)
 
 
 def test_fast_variant_within_tolerance(renderer, port, real_sky, builtin_objects):
