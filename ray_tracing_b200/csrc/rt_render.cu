@@ -65,12 +65,7 @@ __device__ __forceinline__ bool cell_of(const RtRenderParams &P, unsigned idx, i
 {
 	unsigned tile = idx >> 5, lane = idx & 31;
 	unsigned tyu = div_magic(tile, P.magic_tiles_x);
-	int tx = (int) (tile - tyu * (unsigned) P.tiles_x);
-	/* tile rows are visited centre-out (mid, mid+1, mid-1, ...): what the camera
-	 * looks at -- long paths -- is started first and the cheap one-ray sky rows at
-	 * the image borders end the launch, which shortens its tail */
-	int mid = (P.tiles_y - 1) >> 1, k = (int) tyu;
-	int ty = (k & 1) ? mid + ((k + 1) >> 1) : mid - (k >> 1);
+	int tx = (int) (tile - tyu * (unsigned) P.tiles_x), ty = (int) tyu;
 	cx = tx * RT_TILE_W + (int) (lane & (RT_TILE_W - 1));
 	int ly = ty * RT_TILE_H + (int) (lane / RT_TILE_W);     /* row among the rows this launch owns */
 	/* owned rows -> band rows: blocks of 1 << il_shift rows dealt round robin */
