@@ -59,3 +59,25 @@ def gather_bands(band, h: int, w: int, scale: int, rank: int, world: int, dist, 
     for (r0, r1), part in zip(bands, recv):
         full[r0:r1] = part[: r1 - r0]
     return full
+
+
+INTERLEAVE_ROWS = 16  # rt_api.cu: RT_INTERLEAVE_ROWS
+
+
+def owned_rows(h: int, scale: int, rank: int, world: int):
+    """Output rows rendered by `rank` under the round-robin block split used for
+    shared frames (`interleave_count` / `interleave_index` of RtRenderOpts,
+    rt_api.cu: interleave_shift / launch_band): low-res rows are dealt in blocks
+    of 16/scale rows (4 for scales that do not divide 16), block b to rank
+    b % world.  Rows >= (h // scale) * scale are never written (main.c:285-290)."""
+    per = INTERLEAVE_ROWS // scale if 1 <= scale <= INTERLEAVE_ROWS and INTERLEAVE_ROWS % scale == 0 else 4
+    shift = 0
+    while (1 << shift) < per:
+        shift += 1
+    per = 1 << shift
+    lh = h // scale
+    rows = []
+    for j in range(lh):
+        if (j // per) % world == rank:
+            rows.extend(range(j * scale, (j + 1) * scale))
+    return rows

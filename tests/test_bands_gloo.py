@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from ray_tracing_b200.distributed import all_bands, band_rows, gather_bands
+from ray_tracing_b200.distributed import all_bands, band_rows, gather_bands, owned_rows
 
 
 @pytest.mark.parametrize("h,scale,world", [(1080, 1, 8), (1080, 16, 8), (2160, 1, 4), (90, 4, 3), (17, 2, 2), (8, 8, 4)])
@@ -24,6 +24,23 @@ def test_bands_tile_the_frame(h, scale, world):
         assert r0 % scale == 0 and (r1 % scale == 0 or r1 == h)
     sizes = [(r1 - r0 + scale - 1) // scale for r0, r1 in bands]
     assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.parametrize("h,scale,world", [(2160, 1, 8), (1080, 16, 8), (1080, 4, 3), (360, 3, 2), (200, 8, 5)])
+def test_interleaved_blocks_partition_the_frame(h, scale, world):
+    seen = np.zeros(h, np.int32)
+    sizes = []
+    for r in range(world):
+        rows = owned_rows(h, scale, r, world)
+        seen[rows] += 1
+        sizes.append(len(rows))
+    covered = (h // scale) * scale
+    assert (seen[:covered] == 1).all() and (seen[covered:] == 0).all()
+    block = 16 if 16 % scale == 0 else 4 * scale
+    assert max(sizes) - min(sizes) <= block
+    # ownership in OUTPUT rows does not depend on the scale of a progressive sweep
+    if 16 % scale == 0:
+        assert owned_rows(h, scale, 0, world)[: 16] == owned_rows(h, 1, 0, world)[: 16]
 
 
 def _free_port():

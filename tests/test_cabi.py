@@ -73,3 +73,14 @@ def test_fails_loudly_without_gpu():
     fb = np.zeros((4, 4, 3), np.float32)
     rc = host.load_library().render_frame_cuda(ctypes.byref(sc), ctypes.byref(cam), fb.ctypes.data, 4, 4, 1)
     assert rc == -1
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    """No pure-Python or CPU rendering path: without the built .so the binding raises."""
+    monkeypatch.setattr(host, "_lib", None)
+    monkeypatch.setattr(host, "LIB_PATH", os.path.join(ROOT, "ray_tracing_b200", "does_not_exist.so"))
+    with pytest.raises(ImportError) as e:
+        host.load_library()
+    assert "no pure-Python or CPU rendering path" in str(e.value)
+    with pytest.raises(ImportError):
+        host.Renderer(num_gpus=1)

@@ -457,7 +457,11 @@ def test_interleaved_blocks_into_shared_host_frame(renderer, small_sky, builtin_
     frame = np.full((H, W, 3), -1.0, np.float32)
     for rank in range(3):
         renderer.render_into(Camera(), frame.ctypes.data, W, H, host=True, scale=1, interleave_count=3, interleave_index=rank)
-        owned = np.array([(y // 16) % 3 <= rank for y in range(H)])
+        from ray_tracing_b200.distributed import owned_rows
+
+        owned = np.zeros(H, bool)
+        for rr in range(rank + 1):
+            owned[owned_rows(H, 1, rr, 3)] = True
         assert (frame[~owned] == -1.0).all() and (frame[owned] != -1.0).any()
     assert np.array_equal(bits(frame), bits(full))
 
