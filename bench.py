@@ -237,7 +237,7 @@ def main_gpu(args):
     cam = host.Camera()
     variant = host.RT_VARIANT_FAST if args.variant == "fast" else host.RT_VARIANT_EXACT
     kernel = {"auto": host.RT_KERNEL_AUTO, "pixel": host.RT_KERNEL_PIXEL, "persistent": host.RT_KERNEL_PERSISTENT,
-              "wavefront": host.RT_KERNEL_WAVEFRONT}[args.kernel]
+              "wavefront": host.RT_KERNEL_WAVEFRONT, "queued": host.RT_KERNEL_QUEUED}[args.kernel]
 
     r0, r1 = band_rows(H, 1, rank, world)
     band = torch.empty((max(r1 - r0, 1), W, 3), dtype=torch.float32, device=dev)
@@ -434,7 +434,8 @@ def main_gpu(args):
             "clocks": clocks,
             "roofline": {
                 "bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                "traffic": traffic, "kernel": "render_persistent_kernel" if args.kernel != "pixel" else "render_pixel_kernel",
+                "traffic": traffic, "kernel": {"auto": "render_queued_kernel", "queued": "render_queued_kernel", "persistent": "render_persistent_kernel",
+                                                            "wavefront": "render_wavefront_kernel", "pixel": "render_pixel_kernel"}[args.kernel],
                 "kernel_ms": kern_ms, "flops_per_ray": FLOPS_PER_RAY[SCENE], "rays_per_launch": kern_rays,
                 "peak_source": "measured live: register-only %s chains on this GPU" % ("MUL+ADD (no-FMA exact build)" if variant == host.RT_VARIANT_EXACT else "FMA"),
                 "fp32_fma_peak_tflops": fma_peak, "fp32_muladd_peak_tflops": muladd_peak,
@@ -485,7 +486,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--variant", default="exact", choices=["exact", "fast"])
-    ap.add_argument("--kernel", default="auto", choices=["auto", "pixel", "persistent", "wavefront"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "pixel", "persistent", "wavefront", "queued"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--composite", default="p2p", choices=["p2p", "nccl"], help="N>1: how bands reach rank 0")
     args = ap.parse_args()

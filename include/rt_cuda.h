@@ -176,7 +176,8 @@ enum { RT_MEM_AUTO = 0, RT_MEM_HOST = 1, RT_MEM_DEVICE = 2 };
 enum { RT_KERNEL_AUTO = 0,
        RT_KERNEL_PIXEL = 1,       /* one thread per low-res pixel, runs its whole path */
        RT_KERNEL_PERSISTENT = 2,  /* persistent warps, lanes refill with new pixels as paths end */
-       RT_KERNEL_WAVEFRONT = 3 }; /* per-CTA path pool in shared memory, phases over compacted lists */
+       RT_KERNEL_WAVEFRONT = 3,   /* per-warp path pool in shared memory, phases over compacted lists */
+       RT_KERNEL_QUEUED = 4 };    /* persistent warps + per-warp shared-memory queues for finishing / preparing pixels */
 
 typedef struct {
 	uint32_t struct_size;   /* = sizeof(RtRenderOpts) */

@@ -34,19 +34,22 @@ struct SharedScene {
 	int2   *runs;             /* type runs of the scene (rt_device.cuh: nearest_linear) */
 };
 
+/* `smem` = start of the scene area: kernels that keep per-warp queues in shared
+ * memory put them FIRST, so that every address below is the block's base plus a
+ * constant (only `runs` depends on the scene size) and costs no registers. */
 __device__ __forceinline__ SharedScene stage_scene(const RtRenderParams &P, unsigned char *smem, bool linear)
 {
 	SharedScene s;
 	s.lut = reinterpret_cast<float *>(smem);
 	s.sweep = smem + 256 * sizeof(float) + 32 * (threadIdx.x >> 5);
 	s.A = reinterpret_cast<float4 *>(smem + 256 * sizeof(float) + RT_BLOCK_THREADS);
-	s.B = s.A + (linear ? P.scene.n : 0);
-	s.runs = reinterpret_cast<int2 *>(s.B + (linear ? P.scene.n : 0));
+	s.B = s.A + 1;            /* records interleaved: A[2*i], B[2*i] are neighbours (one address per object) */
+	s.runs = reinterpret_cast<int2 *>(s.A + (linear ? 2 * P.scene.n : 0));
 	for (int i = threadIdx.x; i < 256; i += blockDim.x) s.lut[i] = __ldg(&P.byte_lut[i]);
 	if (linear)
 		for (int i = threadIdx.x; i < P.scene.n; i += blockDim.x) {
-			s.A[i] = __ldg(&P.scene.geomA[i]);
-			s.B[i] = __ldg(&P.scene.geomB[i]);
+			s.A[2 * i] = __ldg(&P.scene.geomA[i]);
+			s.B[2 * i] = __ldg(&P.scene.geomB[i]);
 		}
 	if (linear)
 		for (int i = threadIdx.x; i < P.scene.num_runs; i += blockDim.x) s.runs[i] = P.scene.runs[i];
@@ -195,7 +198,7 @@ __device__ __forceinline__ void count_rays(const RtRenderParams &P, unsigned ray
  * ray (launch).  Must be called by all 32 lanes.  Returns 1 for lanes that
  * traced a ray.
  */
-template <bool LBVH>
+template <bool LBVH, bool DEFER_SKY = false>
 __device__ __forceinline__ unsigned warp_step(Path &p, const RtRenderParams &P, const SharedScene &S)
 {
 	unsigned traced = 0;
@@ -207,10 +210,10 @@ __device__ __forceinline__ unsigned warp_step(Path &p, const RtRenderParams &P, 
 		if (LBVH) h = nearest_lbvh(P.bvh, P.scene.geomA, P.scene.geomB, ro, dn, q);
 		else      h = nearest_linear(S.A, S.B, S.runs, P.scene.num_runs, P.scene.n, ro, dn, q, P.scene.div_safe);
 		traced = 1;
-		path_classify(p, h, dn, P.scene, P.sky, S.lut,
+		path_classify<DEFER_SKY>(p, h, dn, P.scene, P.sky, S.lut,
 		              [&](const Hit &hh, f3 d, f3 &point, f3 &normal) {
 			              if (LBVH) surface_of(hh, __ldg(&P.scene.geomA[hh.obj]), __ldg(&P.scene.geomB[hh.obj]), ro, d, point, normal);
-			              else      surface_of(hh, S.A[hh.obj], S.B[hh.obj], ro, d, point, normal);
+			              else      surface_of(hh, S.A[2 * hh.obj], S.B[2 * hh.obj], ro, d, point, normal);
 		              });
 	}
 	warp_sweep(p, S.sweep, P.sweep_tau2);
@@ -317,6 +320,208 @@ render_persistent_kernel(const __grid_constant__ RtRenderParams P)
 			continue;       /* only clipped cells were handed out; fetch more */
 		}
 		rays += warp_step<LBVH>(p, P, S);
+	}
+	count_rays(P, rays);
+}
+
+/* ------------------------------------------- persistent kernel with queues */
+
+/*
+ * render_queued_kernel: the persistent kernel, except that the two things a
+ * lane does BETWEEN paths no longer run with whichever few lanes happen to be
+ * between paths in that warp step (ncu on the plain persistent kernel: sky lookup
+ * 7.5, pixel store 8.5, cell geometry / camera ray / RNG key 8.2 of 32 lanes per
+ * instruction, together 14 % of the issue slots):
+ *
+ *   finish   a lane whose path ended pushes (sky direction, contrib, result,
+ *            pixel) onto its warp's stack in shared memory and is free at once;
+ *            whenever 32 entries wait, the whole warp does the sky lookups
+ *            (gpu_and_windowing.c:42-112), the clamp (main.c:267-269) and the
+ *            stores (main.c:305-310, 394, 476) together;
+ *   refill   the warp prepares a whole tile of 32 pixels at a time (cell
+ *            geometry main.c:293-303, camera ray camera.c:121, RNG key) and parks
+ *            them in shared memory; lanes pop one as their paths end.
+ *
+ * Paths stay in registers (unlike the wavefront kernel), the per-path arithmetic
+ * is the same device code, every pixel is still finished exactly once: frames
+ * and ray counts are identical to the other kernels'.
+ */
+#define RQ_FIN_CAP    64        /* at most 31 waiting + 32 pushed in one step */
+#define RQ_FIN_WORDS  12
+#define RQ_PREP_WORDS 8
+#define RQ_WARP_WORDS (RQ_FIN_WORDS * RQ_FIN_CAP + RQ_PREP_WORDS * 32)
+#define RQ_BLOCK_BYTES (sizeof(float) * RQ_WARP_WORDS * (RT_BLOCK_THREADS / 32))
+
+enum { RQ_DIR = 0, RQ_CONTRIB = 3, RQ_RESULT = 6, RQ_X0 = 9, RQ_Y0 = 10, RQ_FLAGS = 11 };
+enum { RQP_D = 0, RQP_RNGLO = 3, RQP_RNGHI = 4, RQP_X0 = 5, RQP_Y0 = 6, RQP_TW = 7 };
+#define RQ_ESCAPED 256u         /* RQ_FLAGS: tile width | RQ_ESCAPED when the sky lookup is still due */
+
+/* finish `n` (<= 32) entries from the top of the warp's stack; all lanes call */
+__device__ __forceinline__ void rq_drain(const RtRenderParams &P, const SharedScene &S, const float *fin, int top, int n)
+{
+	const int lane = threadIdx.x & 31;
+	const bool has = lane < n;
+	const int e = top - n + lane;
+	Cell c;
+	c.x0 = c.y0 = c.tw = 0;
+	c.u = c.v = 0.0f;
+	f3 color = mk(0.0f, 0.0f, 0.0f);
+	if (has) {
+		const unsigned *fu = reinterpret_cast<const unsigned *>(fin);
+		unsigned flags = fu[RQ_FLAGS * RQ_FIN_CAP + e];
+		f3 res = mk(fin[(RQ_RESULT + 0) * RQ_FIN_CAP + e], fin[(RQ_RESULT + 1) * RQ_FIN_CAP + e], fin[(RQ_RESULT + 2) * RQ_FIN_CAP + e]);
+		if (flags & RQ_ESCAPED) {                      /* main.c:162-173 */
+			f3 dn = mk(fin[(RQ_DIR + 0) * RQ_FIN_CAP + e], fin[(RQ_DIR + 1) * RQ_FIN_CAP + e], fin[(RQ_DIR + 2) * RQ_FIN_CAP + e]);
+			f3 contrib = mk(fin[(RQ_CONTRIB + 0) * RQ_FIN_CAP + e], fin[(RQ_CONTRIB + 1) * RQ_FIN_CAP + e], fin[(RQ_CONTRIB + 2) * RQ_FIN_CAP + e]);
+			f3 skyc = sky_lookup(P.sky, S.lut, dn);
+			res = add3(res, mul3(skyc, contrib));
+		}
+		color = mk(clamp01(res.x), clamp01(res.y), clamp01(res.z));      /* main.c:267-269 */
+		c.x0 = (int) fu[RQ_X0 * RQ_FIN_CAP + e];
+		c.y0 = (int) fu[RQ_Y0 * RQ_FIN_CAP + e];
+		c.tw = (int) (flags & 255u);
+	}
+	if (P.scale >= 4) store_cells_warp(P, has, c, color);   /* warp-uniform */
+	else if (has) store_cell(P, c, color);
+}
+
+#ifndef RT_QUEUED_MIN_BLOCKS
+#define RT_QUEUED_MIN_BLOCKS 6
+#endif
+
+template <bool LBVH>
+__global__ void __launch_bounds__(RT_BLOCK_THREADS, LBVH ? 8 : RT_QUEUED_MIN_BLOCKS)
+render_queued_kernel(const __grid_constant__ RtRenderParams P)
+{
+	extern __shared__ __align__(16) unsigned char smem[];
+	SharedScene S = stage_scene(P, smem + RQ_BLOCK_BYTES, !LBVH);
+	float *fin = reinterpret_cast<float *>(smem) + (size_t) (threadIdx.x >> 5) * RQ_WARP_WORDS;
+	float *prep = fin + RQ_FIN_WORDS * RQ_FIN_CAP;
+	unsigned *finu = reinterpret_cast<unsigned *>(fin), *prepu = reinterpret_cast<unsigned *>(prep);
+
+	const unsigned full = 0xffffffffu;
+	const unsigned lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
+	const unsigned total = (unsigned) (P.tiles_x * P.tiles_y) * 32u;
+
+	Path p;
+	p.mode = MODE_IDLE;
+	p.obj = 0;
+	int cx0 = 0, cy0 = 0, ctw = 0;  /* output tile of the lane's pixel */
+	bool owns = false;              /* lane holds a pixel whose path is running or just ended */
+	unsigned rays = 0;
+	int fin_n = 0, prep_n = 0;                /* warp-uniform stack heights */
+	unsigned batch_next = 0, batch_end = 0;   /* warp-uniform: tile-ordered pixel indices, multiples of 32 */
+	bool exhausted = false;                   /* warp-uniform */
+
+	for (;;) {
+		unsigned idle = __ballot_sync(full, p.mode == MODE_IDLE);
+		if (idle) {
+			/* ---- finish: push the ended paths, drain when a full warp's worth waits ---- */
+			const bool ended = p.mode == MODE_IDLE && owns;
+			unsigned em = __ballot_sync(full, ended);
+			if (em) {
+				if (ended) {
+					int e = fin_n + (int) __popc(em & lt);
+					const bool escaped = p.obj < 0;
+					if (escaped) {
+						fin[(RQ_DIR + 0) * RQ_FIN_CAP + e] = p.point.x;
+						fin[(RQ_DIR + 1) * RQ_FIN_CAP + e] = p.point.y;
+						fin[(RQ_DIR + 2) * RQ_FIN_CAP + e] = p.point.z;
+						fin[(RQ_CONTRIB + 0) * RQ_FIN_CAP + e] = p.contrib.x;
+						fin[(RQ_CONTRIB + 1) * RQ_FIN_CAP + e] = p.contrib.y;
+						fin[(RQ_CONTRIB + 2) * RQ_FIN_CAP + e] = p.contrib.z;
+					}
+					fin[(RQ_RESULT + 0) * RQ_FIN_CAP + e] = p.result.x;
+					fin[(RQ_RESULT + 1) * RQ_FIN_CAP + e] = p.result.y;
+					fin[(RQ_RESULT + 2) * RQ_FIN_CAP + e] = p.result.z;
+					finu[RQ_X0 * RQ_FIN_CAP + e] = (unsigned) cx0;
+					finu[RQ_Y0 * RQ_FIN_CAP + e] = (unsigned) cy0;
+					finu[RQ_FLAGS * RQ_FIN_CAP + e] = (unsigned) ctw | (escaped ? RQ_ESCAPED : 0u);
+					owns = false;
+				}
+				fin_n += (int) __popc(em);
+				__syncwarp();
+			}
+			/* ---- refill: idle lanes pop prepared pixels; a tile is prepared when none is left ---- */
+			unsigned want = idle;
+			while (want) {
+				if (prep_n == 0) {
+					if (batch_next == batch_end) {
+						if (exhausted) break;
+						/* guided self-scheduling: big batches while plenty of work is left,
+						 * single tiles at the end (see render_persistent_kernel) */
+						unsigned base = 0, claim = 0;
+						if (lane == 0) {
+							unsigned seen = *(volatile unsigned *) P.work_counter;
+							unsigned left = seen < total ? (total - seen) >> 5 : 0;
+							unsigned warps = gridDim.x * (RT_BLOCK_THREADS / 32);
+							claim = min(max(left / (4u * warps), 1u), (unsigned) RT_WARP_BATCH) * 32u;
+							base = atomicAdd(P.work_counter, claim);
+						}
+						base = __shfl_sync(full, base, 0);
+						claim = __shfl_sync(full, claim, 0);
+						if (base >= total) { exhausted = true; break; }
+						batch_next = base;
+						batch_end = min(base + claim, total);
+					}
+					int cx, cy;
+					const bool ok = cell_of(P, batch_next + lane, cx, cy);
+					batch_next += 32;
+					unsigned om = __ballot_sync(full, ok);
+					if (ok) {
+						Cell c = cell_geometry(P, cx, cy);
+						f3 d = camera_dir(P.cam, c.u, c.v);
+						uint64_t key = pixel_key(c.u, c.v, P.pass_mix);
+						int e = (int) __popc(om & lt);
+						prep[(RQP_D + 0) * 32 + e] = d.x;
+						prep[(RQP_D + 1) * 32 + e] = d.y;
+						prep[(RQP_D + 2) * 32 + e] = d.z;
+						prepu[RQP_RNGLO * 32 + e] = (unsigned) key;
+						prepu[RQP_RNGHI * 32 + e] = (unsigned) (key >> 32);
+						prepu[RQP_X0 * 32 + e] = (unsigned) c.x0;
+						prepu[RQP_Y0 * 32 + e] = (unsigned) c.y0;
+						prepu[RQP_TW * 32 + e] = (unsigned) c.tw;
+					}
+					prep_n = (int) __popc(om);
+					__syncwarp();
+					if (prep_n == 0) continue;          /* a tile of clipped cells only */
+				}
+				const bool mine = (want >> lane) & 1u;
+				const int rank = (int) __popc(want & lt);
+				const int n = min((int) __popc(want), prep_n);
+				if (mine && rank < n) {
+					int e = prep_n - 1 - rank;
+					p.d = mk(prep[(RQP_D + 0) * 32 + e], prep[(RQP_D + 1) * 32 + e], prep[(RQP_D + 2) * 32 + e]);
+					p.rng = ((uint64_t) prepu[RQP_RNGHI * 32 + e] << 32) | prepu[RQP_RNGLO * 32 + e];
+					cx0 = (int) prepu[RQP_X0 * 32 + e];
+					cy0 = (int) prepu[RQP_Y0 * 32 + e];
+					ctw = (int) prepu[RQP_TW * 32 + e];
+					/* path_begin (main.c:135-156) with the prepared ray and key */
+					p.ray_o = mk(P.cam.origin);
+					p.ray_d = p.d;
+					p.contrib = mk(1.0f, 1.0f, 1.0f);
+					p.result = mk(0.0f, 0.0f, 0.0f);
+					p.bounce = 0;
+					p.shadow = false;
+					p.obj = 0;
+					p.mode = MODE_TRACE;
+					owns = true;
+				}
+				want = __ballot_sync(full, mine && rank >= n);
+				prep_n -= n;
+				__syncwarp();
+			}
+		}
+		/* nothing runs and nothing is left to hand out: the launch is over for this warp */
+		const bool over = __ballot_sync(full, p.mode != MODE_IDLE) == 0;
+		while (fin_n >= 32 || (over && fin_n > 0)) {    /* the ONE finishing site */
+			int n = min(fin_n, 32);
+			rq_drain(P, S, fin, fin_n, n);
+			fin_n -= n;
+			__syncwarp();
+		}
+		if (over) break;
+		rays += warp_step<LBVH, true>(p, P, S);
 	}
 	count_rays(P, rays);
 }
@@ -557,7 +762,7 @@ render_wavefront_kernel(const __grid_constant__ RtRenderParams P)
 				} else {
 					f3 point, normal;
 					if (LBVH) surface_of(h, __ldg(&P.scene.geomA[h.obj]), __ldg(&P.scene.geomB[h.obj]), ro, dn, point, normal);
-					else      surface_of(h, S.A[h.obj], S.B[h.obj], ro, dn, point, normal);
+					else      surface_of(h, S.A[2 * h.obj], S.B[2 * h.obj], ro, dn, point, normal);
 					pool.u(WF_OBJ, s) = (unsigned) h.obj;
 					pool.set3(WF_POINT, s, point);
 					pool.set3(WF_NORMAL, s, normal);
@@ -726,6 +931,11 @@ static size_t wavefront_smem_bytes(const RtRenderParams &P, bool lbvh)
 	return scene + (sizeof(float) * WF_WORDS * WF_PATHS + 3 * 2 * WF_PATHS) * WF_WARPS;
 }
 
+static size_t queued_smem_bytes(const RtRenderParams &P, bool lbvh)
+{
+	return RQ_BLOCK_BYTES + smem_bytes(P, lbvh);
+}
+
 extern "C" cudaError_t RT_FN(launch_render)(const RtRenderParams *P, int lbvh, int persistent,
                                              int grid_blocks, cudaStream_t stream)
 {
@@ -734,6 +944,17 @@ extern "C" cudaError_t RT_FN(launch_render)(const RtRenderParams *P, int lbvh, i
 	unsigned total = (unsigned) (P->tiles_x * P->tiles_y) * 32u;
 	if (total == 0) return cudaSuccess;
 	cudaError_t e;
+	if (persistent == 3) {      /* persistent kernel with finish / refill queues */
+		size_t qsm = queued_smem_bytes(*P, lbvh != 0);
+		if (lbvh) {
+			if ((e = allow_smem(render_queued_kernel<true>, qsm)) != cudaSuccess) return e;
+			render_queued_kernel<true><<<grid_blocks, RT_BLOCK_THREADS, qsm, stream>>>(*P);
+		} else {
+			if ((e = allow_smem(render_queued_kernel<false>, qsm)) != cudaSuccess) return e;
+			render_queued_kernel<false><<<grid_blocks, RT_BLOCK_THREADS, qsm, stream>>>(*P);
+		}
+		return cudaGetLastError();
+	}
 	if (persistent == 2) {      /* wavefront kernel: one CTA per SM, paths pooled in shared memory */
 		size_t wsm = wavefront_smem_bytes(*P, lbvh != 0);
 		if (lbvh) {
@@ -781,12 +1002,21 @@ extern "C" cudaError_t RT_FN(wavefront_blocks_per_sm)(const RtRenderParams *P, i
 
 extern "C" int RT_FN(wavefront_paths_per_block)(void) { return WF_PATHS * WF_WARPS; }
 
-/* occupancy query for sizing the persistent grid */
-extern "C" cudaError_t RT_FN(persistent_blocks_per_sm)(const RtRenderParams *P, int lbvh, int *out)
+/* occupancy query for sizing the persistent grid (queued != 0: render_queued_kernel) */
+extern "C" cudaError_t RT_FN(persistent_blocks_per_sm)(const RtRenderParams *P, int lbvh, int queued, int *out)
 {
 	using namespace RT_NS;
 	size_t sm = smem_bytes(*P, lbvh != 0);
 	cudaError_t e;
+	if (queued) {
+		sm = queued_smem_bytes(*P, lbvh != 0);
+		if (lbvh) {
+			if ((e = allow_smem(render_queued_kernel<true>, sm)) != cudaSuccess) return e;
+			return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, render_queued_kernel<true>, RT_BLOCK_THREADS, sm);
+		}
+		if ((e = allow_smem(render_queued_kernel<false>, sm)) != cudaSuccess) return e;
+		return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, render_queued_kernel<false>, RT_BLOCK_THREADS, sm);
+	}
 	if (lbvh) {
 		if ((e = allow_smem(render_persistent_kernel<true>, sm)) != cudaSuccess) return e;
 		return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, render_persistent_kernel<true>, RT_BLOCK_THREADS, sm);

@@ -26,7 +26,7 @@ RT_FB_F32X3, RT_FB_U8X4 = 0, 1
 RT_VARIANT_EXACT, RT_VARIANT_FAST = 0, 1
 RT_TRAVERSAL_AUTO, RT_TRAVERSAL_LINEAR, RT_TRAVERSAL_LBVH = 0, 1, 2
 RT_MEM_AUTO, RT_MEM_HOST, RT_MEM_DEVICE = 0, 1, 2
-RT_KERNEL_AUTO, RT_KERNEL_PIXEL, RT_KERNEL_PERSISTENT, RT_KERNEL_WAVEFRONT = 0, 1, 2, 3
+RT_KERNEL_AUTO, RT_KERNEL_PIXEL, RT_KERNEL_PERSISTENT, RT_KERNEL_WAVEFRONT, RT_KERNEL_QUEUED = 0, 1, 2, 3, 4
 RT_UP, RT_DOWN, RT_LEFT, RT_RIGHT = 0, 1, 2, 3
 RT_LBVH_THRESHOLD = 64
 

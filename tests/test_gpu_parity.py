@@ -14,12 +14,12 @@ import pytest
 
 from conftest import GOLDEN, random_scene
 from ray_tracing_b200 import host, scenes
-from ray_tracing_b200.host import (RT_FB_U8X4, RT_KERNEL_PERSISTENT, RT_KERNEL_PIXEL, RT_KERNEL_WAVEFRONT, RT_TRAVERSAL_LBVH,
+from ray_tracing_b200.host import (RT_FB_U8X4, RT_KERNEL_AUTO, RT_KERNEL_PERSISTENT, RT_KERNEL_PIXEL, RT_KERNEL_QUEUED, RT_KERNEL_WAVEFRONT, RT_TRAVERSAL_LBVH,
                                    RT_TRAVERSAL_LINEAR, RT_VARIANT_EXACT, RT_VARIANT_FAST, Camera)
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = [RT_KERNEL_PIXEL, RT_KERNEL_PERSISTENT, RT_KERNEL_WAVEFRONT]
+KERNELS = [RT_KERNEL_PIXEL, RT_KERNEL_PERSISTENT, RT_KERNEL_WAVEFRONT, RT_KERNEL_QUEUED]
 
 
 def bits(a):
@@ -327,7 +327,7 @@ def test_progressive_sweep_vs_oracle(renderer, port, small_sky, builtin_objects)
     assert np.array_equal(bits(frame), bits(want))
     assert st["rays"] == rays
     assert renderer.accum_count() == count
-    for kern in (RT_KERNEL_PIXEL, RT_KERNEL_WAVEFRONT):
+    for kern in (RT_KERNEL_PIXEL, RT_KERNEL_WAVEFRONT, RT_KERNEL_QUEUED):
         other, so = renderer.render_sweep(Camera(), W, H, 16, first_pass=0, kernel=kern)
         assert np.array_equal(bits(other), bits(want)) and so["rays"] == rays
     frame, st = renderer.render_sweep(Camera(), W, H, 16, first_pass=0)
@@ -478,6 +478,20 @@ def test_4k_properties(renderer, port, real_sky, builtin_objects):
     assert np.array_equal(bits(a), bits(b)) and sa["rays"] == sb["rays"]
     c, _ = renderer.render_frame(Camera(), W, H, 1, kernel=RT_KERNEL_PERSISTENT)
     assert np.array_equal(bits(a), bits(c))
+    # the default (queued) kernel into a frame full of sentinels: every pixel is
+    # finished exactly once, whatever is left in the warps' stacks when work runs out
+    import torch
+
+    frame = torch.full((H, W, 3), -1.0, dtype=torch.float32, device="cuda")
+    for kern, rows in ((RT_KERNEL_QUEUED, None), (RT_KERNEL_AUTO, (16, 2144))):
+        frame.fill_(-1.0)
+        sq = renderer.render_into(Camera(), frame.data_ptr(), W, H, stats=True, scale=1, kernel=kern, rows=rows)
+        got = frame.cpu().numpy()
+        r0, r1 = rows or (0, H)
+        assert np.array_equal(bits(got[r0:r1]), bits(a[r0:r1]))
+        assert (got[:r0] == -1.0).all() and (got[r1:] == -1.0).all()
+        if rows is None:
+            assert sq["rays"] == sa["rays"]
     world = port.world(builtin_objects[0], real_sky)
     for r0 in (0, 1000, 2100):
         want = np.zeros((H, W, 3), np.float32)
@@ -496,8 +510,9 @@ def test_lbvh_equals_linear_scan_frames(renderer, small_sky):
     a, sa = renderer.render_frame(Camera(), 480, 270, 1, traversal=RT_TRAVERSAL_LINEAR)
     b, sb = renderer.render_frame(Camera(), 480, 270, 1, traversal=RT_TRAVERSAL_LBVH)
     assert np.array_equal(bits(a), bits(b)) and sa["rays"] == sb["rays"]
-    c, sc = renderer.render_frame(Camera(), 480, 270, 1, traversal=RT_TRAVERSAL_LBVH, kernel=RT_KERNEL_WAVEFRONT)
-    assert np.array_equal(bits(a), bits(c)) and sa["rays"] == sc["rays"]
+    for kern in (RT_KERNEL_WAVEFRONT, RT_KERNEL_QUEUED):
+        c, sc = renderer.render_frame(Camera(), 480, 270, 1, traversal=RT_TRAVERSAL_LBVH, kernel=kern)
+        assert np.array_equal(bits(a), bits(c)) and sa["rays"] == sc["rays"]
 
 
 def test_large_scene_lbvh_vs_oracle(renderer, port, small_sky):
