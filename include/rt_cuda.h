@@ -278,6 +278,10 @@ size_t rt_cuda_param_bytes(void);
 /* Test knob: tau^2 of the sign shortcut in the light-sample sweep (negative =
  * default 4e-12).  1e30 forces the literal path; frames must be identical. */
 int rt_cuda_debug_set_sweep_threshold(float tau2);
+/* Test knob: 0 = RT_KERNEL_QUEUED keeps tiles in image order; 1 (default) = a pose rendered
+ * repeatedly is scheduled longest tiles first from the costs its previous pass recorded.
+ * Scheduling only: frames must be identical either way. */
+int rt_cuda_debug_set_tile_schedule(int on);
 /* Bit-compare the render kernels' hoisted-reciprocal division with IEEE `/` on
  * blocks*256*per_thread operand pairs (exponent ranges given); see rt_device.cuh. */
 int rt_cuda_debug_div_check(uint64_t seed, unsigned blocks, unsigned per_thread, int lo_exp_b, int hi_exp_b,

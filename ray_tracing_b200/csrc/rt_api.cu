@@ -67,6 +67,14 @@ extern "C" const char *rt_cuda_last_error(void) { return g_err; }
 /* ----------------------------------------------------------------- context */
 
 #define RT_MAX_GPUS 16
+#define RT_WORK_SLOTS 8       /* tile counters: launches that may be in flight at once on one GPU */
+
+/* What a tile schedule is valid for: the same pixels at the same cost. */
+struct TileKey {
+	int      w, h, scale, ncols, r0, r1, il_n, il_i, lbvh;
+	unsigned scene_epoch;
+	RtCamera cam;
+};
 
 struct DeviceCtx {
 	int          device = -1;
@@ -85,8 +93,15 @@ struct DeviceCtx {
 	float  *accum = nullptr;    size_t accum_bytes = 0;
 	int     accum_w = 0, accum_h = 0, accum_row0 = 0, accum_rows = 0;
 	unsigned long long *ray_counter = nullptr;
-	unsigned int       *work_counter = nullptr;
+	unsigned int       *work_counter = nullptr;   /* RT_WORK_SLOTS counters, one per launch in flight */
+	unsigned            launch_seq = 0;
 	unsigned long long *host_rays = nullptr;              /* pinned */
+	/* longest-tiles-first schedule of the queued kernel (see tile_schedule()) */
+	unsigned int *tile_cost = nullptr, *tile_order = nullptr;
+	size_t        tile_capacity = 0;
+	TileKey       order_key;
+	int           order_state = 0;                        /* 0 none, 1 key seen once, 2 order built */
+	cudaEvent_t   order_ready = nullptr;
 	/* pipelined host read-back: two staging frames + a copy stream */
 	cudaStream_t copy_stream = nullptr;
 	void        *stage[2] = {nullptr, nullptr};
@@ -109,6 +124,8 @@ struct Context {
 	RtScene  *scene_cache = nullptr;    /* copy of the last RtScene given to render_frame_cuda */
 	float     accum_count = 0.0f;       /* accum_counts[] of main.c:89 (all columns advance together) */
 	float     sweep_tau2 = 4e-12f;      /* rt_device.cuh: sample_faces_surface; tests may override */
+	unsigned  scene_epoch = 0;          /* bumped by every scene upload (tile schedules die with the scene) */
+	int       tile_schedule = 1;        /* 0: never reorder tiles (tests / A-B) */
 };
 
 static Context g;
@@ -128,6 +145,9 @@ static void free_device(DeviceCtx &d)
 	cudaFree(d.sky); cudaFree(d.lut);
 	cudaFree(d.fb); cudaFree(d.accum);
 	cudaFree(d.ray_counter); cudaFree(d.work_counter);
+	cudaFree(d.tile_cost); cudaFree(d.tile_order);
+	d.tile_cost = d.tile_order = nullptr; d.tile_capacity = 0; d.order_state = 0;
+	if (d.order_ready) { cudaEventDestroy(d.order_ready); d.order_ready = nullptr; }
 	if (d.host_rays) cudaFreeHost(d.host_rays);
 	for (auto &e : d.ev) if (e) cudaEventDestroy(e);
 	for (int k = 0; k < 2; k++) {
@@ -167,7 +187,7 @@ static int init_devices(const int *devices, int count)
 		}
 		for (auto &ev : d.ev) CU(cudaEventCreate(&ev));
 		CU(cudaMalloc(&d.ray_counter, sizeof(unsigned long long)));
-		CU(cudaMalloc(&d.work_counter, sizeof(unsigned int)));
+		CU(cudaMalloc(&d.work_counter, RT_WORK_SLOTS * sizeof(unsigned int)));
 		CU(cudaMemset(d.ray_counter, 0, sizeof(unsigned long long)));
 		CU(cudaMallocHost(&d.host_rays, sizeof(unsigned long long)));
 		float lut[256];
@@ -289,6 +309,7 @@ extern "C" int rt_cuda_upload_objects(const RtObject *objects, int n)
 	g.div_safe = ps.div_safe;
 	g.num_runs = (int) runs.size();
 	g.have_scene = true;
+	g.scene_epoch++;
 	g.have_bvh = want_bvh;
 	rt_host_free_packed(&ps);
 	cudaSetDevice(g.dev[0].device);
@@ -372,7 +393,7 @@ static bool is_device_pointer(const void *p)
 	return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
-static void fill_views(const DeviceCtx &d, RtRenderParams &P)
+static void fill_views(DeviceCtx &d, RtRenderParams &P)
 {
 	P.scene.geomA = d.geomA;
 	P.scene.geomB = d.geomB;
@@ -390,7 +411,9 @@ static void fill_views(const DeviceCtx &d, RtRenderParams &P)
 	P.sky.face_stride = (size_t) g.sky_w * g.sky_h;
 	P.byte_lut = d.lut;
 	P.ray_counter = d.ray_counter;
-	P.work_counter = d.work_counter;
+	/* every launch gets its own tile counter (zeroed on its stream just before it),
+	 * so that frames rendered on different caller streams may overlap */
+	P.work_counter = d.work_counter + (d.launch_seq++ % RT_WORK_SLOTS);
 }
 
 static int pick_traversal(int requested, bool *lbvh)
@@ -491,6 +514,92 @@ static int copy_owned_blocks(void *dst, const void *src, const PassPlan &pl, int
 	return RT_OK;
 }
 
+/*
+ * Longest tiles first.  A warp of the queued kernel works on 8x4-pixel tiles and
+ * a tile lasts as long as its longest path (1 to 40 rays, each a warp step of
+ * several microseconds), so whatever tiles are handed out last decide how long
+ * the launch drags on after the work has run out (~0.1 ms per launch with tiles
+ * in image order: 5 % of a 4K frame, 30 % of one GPU's share of it at 8 GPUs).
+ * The interactive loop renders the same pose pass after pass (main.c:354-403),
+ * so pass k tells what pass k+1 will cost: the second launch with an unchanged
+ * key records the largest bounce count per tile (one atomicMax per non-sky
+ * pixel), a counting sort turns that into an order (costly tiles first, image
+ * order within a class), and later launches hand tiles out in that order.
+ * Scheduling only -- every pixel is computed by the same code from the same
+ * key, so frames are bit-identical with and without it (test_tile_schedule).
+ */
+#define RT_ORDER_THREADS 512
+__global__ void __launch_bounds__(RT_ORDER_THREADS) tile_order_kernel(const unsigned int *cost, unsigned int *order, unsigned n)
+{
+	__shared__ unsigned cnt[16][RT_ORDER_THREADS];
+	const unsigned t = threadIdx.x;
+	const unsigned chunk = (n + RT_ORDER_THREADS - 1) / RT_ORDER_THREADS;
+	const unsigned lo = min(t * chunk, n), hi = min(lo + chunk, n);
+	for (int b = 0; b < 16; b++) cnt[b][t] = 0;
+	for (unsigned i = lo; i < hi; i++) cnt[min(cost[i], 15u)][t]++;
+	__syncthreads();
+	/* exclusive scan over (class descending, thread ascending) */
+	__shared__ unsigned total[16];
+	if (t < 16) {
+		unsigned run = 0;
+		for (int k = 0; k < RT_ORDER_THREADS; k++) { unsigned c = cnt[t][k]; cnt[t][k] = run; run += c; }
+		total[t] = run;
+	}
+	__syncthreads();
+	unsigned base[16];
+	{
+		unsigned run = 0;
+		for (int b = 15; b >= 0; b--) { base[b] = run; run += total[b]; }
+	}
+	for (unsigned i = lo; i < hi; i++) {
+		unsigned b = min(cost[i], 15u);
+		order[base[b] + cnt[b][t]++] = i;
+	}
+}
+
+/* Decide what this launch does about the schedule; returns 0 = nothing,
+ * 1 = record costs (build_tile_order() must follow the launch), 2 = use the order. */
+static int tile_schedule(DeviceCtx &d, const TileKey &key, size_t tiles, RtRenderParams &P, cudaStream_t stream)
+{
+	P.tile_order = nullptr;
+	P.tile_cost = nullptr;
+	if (!g.tile_schedule || tiles < 2048 || tiles >= (1u << 20)) { d.order_state = 0; return 0; }
+	if (d.order_state == 0 || memcmp(&key, &d.order_key, sizeof(TileKey)) != 0) {
+		d.order_key = key;
+		d.order_state = 1;          /* a moving camera never gets past this: no cost */
+		return 0;
+	}
+	if (d.order_state == 1) {
+		if (d.tile_capacity < tiles) {
+			cudaFree(d.tile_cost); cudaFree(d.tile_order);
+			d.tile_cost = d.tile_order = nullptr; d.tile_capacity = 0;
+			if (cudaMalloc(&d.tile_cost, tiles * sizeof(unsigned)) != cudaSuccess ||
+			    cudaMalloc(&d.tile_order, tiles * sizeof(unsigned)) != cudaSuccess) {
+				cudaGetLastError();
+				cudaFree(d.tile_cost); d.tile_cost = nullptr;
+				return 0;
+			}
+			d.tile_capacity = tiles;
+		}
+		if (!d.order_ready && cudaEventCreateWithFlags(&d.order_ready, cudaEventDisableTiming) != cudaSuccess) return 0;
+		if (cudaMemsetAsync(d.tile_cost, 0, tiles * sizeof(unsigned), stream) != cudaSuccess) return 0;
+		P.tile_cost = d.tile_cost;
+		return 1;
+	}
+	cudaStreamWaitEvent(stream, d.order_ready, 0);     /* the order may have been built on another stream */
+	P.tile_order = d.tile_order;
+	return 2;
+}
+
+static int build_tile_order(DeviceCtx &d, size_t tiles, cudaStream_t stream)
+{
+	tile_order_kernel<<<1, RT_ORDER_THREADS, 0, stream>>>(d.tile_cost, d.tile_order, (unsigned) tiles);
+	CU(cudaGetLastError());
+	CU(cudaEventRecord(d.order_ready, stream));
+	d.order_state = 2;
+	return RT_OK;
+}
+
 /* Launch one pass for one device over output rows [r0, r1) (scale aligned). */
 static int launch_band(DeviceCtx &d, const RtCamera *cam, const PassPlan &pl, const RtRenderOpts *o,
                        void *fb, int fb_row_offset, int r0, int r1, int il_n, int il_i, cudaStream_t stream,
@@ -551,7 +660,7 @@ static int launch_band(DeviceCtx &d, const RtCamera *cam, const PassPlan &pl, co
 	if (P.tiles_x > 0 && P.tiles_y > 0) {
 		int grid = 0;
 		if (pl.wavefront) {
-			CU(cudaMemsetAsync(d.work_counter, 0, sizeof(unsigned int), stream));
+			CU(cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned int), stream));
 			static int wf_per_sm[2][2] = {{0, 0}, {0, 0}}, wf_n[2][2] = {{-1, -1}, {-1, -1}};
 			int &per_sm = wf_per_sm[pl.exact ? 0 : 1][pl.lbvh ? 1 : 0];
 			int &for_n = wf_n[pl.exact ? 0 : 1][pl.lbvh ? 1 : 0];
@@ -567,7 +676,7 @@ static int launch_band(DeviceCtx &d, const RtCamera *cam, const PassPlan &pl, co
 			(*launches)++;
 		} else {
 		if (pl.persistent) {
-			CU(cudaMemsetAsync(d.work_counter, 0, sizeof(unsigned int), stream));
+			CU(cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned int), stream));
 			/* occupancy of the persistent kernel, queried once per (variant, traversal, scene size) */
 			static int cached_per_sm[2][2][2] = {{{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}};
 			static int cached_n[2][2][2] = {{{-1, -1}, {-1, -1}}, {{-1, -1}, {-1, -1}}};
@@ -582,8 +691,23 @@ static int launch_band(DeviceCtx &d, const RtCamera *cam, const PassPlan &pl, co
 			unsigned blocks_needed = (warps_needed + (RT_BLOCK_THREADS / 32) - 1) / (RT_BLOCK_THREADS / 32);
 			grid = (int) std::min<unsigned>((unsigned) (d.sm_count * per_sm), blocks_needed);
 		}
+		int sched = 0;
+		size_t tiles = (size_t) P.tiles_x * P.tiles_y;
+		if (pl.queued) {
+			TileKey key;
+			memset(&key, 0, sizeof(key));
+			key.w = pl.w; key.h = pl.h; key.scale = pl.scale; key.ncols = pl.ncols; key.r0 = r0; key.r1 = r1;
+			key.il_n = P.il_n; key.il_i = P.il_i; key.lbvh = pl.lbvh; key.scene_epoch = g.scene_epoch;
+			key.cam.pos = cam->pos; key.cam.front = cam->front; key.cam.up = cam->up; key.cam.fov = cam->fov;
+			sched = tile_schedule(d, key, tiles, P, stream);
+		}
 		CU((pl.exact ? rt_exact_launch_render : rt_fast_launch_render)(&P, pl.lbvh, pl.queued ? 3 : (pl.persistent ? 1 : 0), grid, stream));
 		(*launches)++;
+		if (sched == 1) {
+			int rc = build_tile_order(d, tiles, stream);
+			if (rc != RT_OK) return rc;
+			(*launches)++;
+		}
 		}
 	}
 
@@ -622,7 +746,7 @@ static int render_pass(const RtCamera *cam, void *fb, int w, int h, const RtRend
 	/* AUTO: the queued kernel for linear-scan scenes (4K scene_0: 2.06 ms against
 	 * 2.20 ms persistent), the plain persistent kernel for LBVH scenes (same speed,
 	 * less shared memory) */
-	pl.queued = o->kernel == RT_KERNEL_QUEUED || (o->kernel == RT_KERNEL_AUTO && !pl.lbvh);
+	pl.queued = (o->kernel == RT_KERNEL_QUEUED || (o->kernel == RT_KERNEL_AUTO && !pl.lbvh)) && o->scale <= 64;   /* tile width is packed into 7 bits */
 	pl.persistent = o->kernel == RT_KERNEL_PERSISTENT || o->kernel == RT_KERNEL_AUTO || pl.queued;
 	pl.wavefront = o->kernel == RT_KERNEL_WAVEFRONT;
 
@@ -1123,6 +1247,16 @@ extern "C" int rt_cuda_copy_to_host(void *host_dst, const void *dev_src, size_t 
 extern "C" int rt_cuda_debug_set_sweep_threshold(float tau2)
 {
 	g.sweep_tau2 = tau2 >= 0.0f ? tau2 : 4e-12f;
+	return RT_OK;
+}
+
+/* Test / A-B knob: 0 keeps the queued kernel's tiles in image order (no cost
+ * recording, no reordering), 1 (default) lets repeated poses be scheduled
+ * longest tiles first.  Results never depend on it. */
+extern "C" int rt_cuda_debug_set_tile_schedule(int on)
+{
+	g.tile_schedule = on ? 1 : 0;
+	for (int i = 0; i < g.ngpu; i++) g.dev[i].order_state = 0;
 	return RT_OK;
 }
 

@@ -81,6 +81,12 @@ struct RtRenderParams {
 
 	unsigned long long *ray_counter;
 	unsigned int       *work_counter;   /* persistent kernel: next tile-ordered pixel */
+
+	/* render_queued_kernel: longest-tiles-first schedule (rt_api.cu: tile order).
+	 * tile_order[k] = tile handed out k-th (NULL: natural order); tile_cost[t] =
+	 * largest bounce count of a path of tile t, recorded when non-NULL. */
+	const unsigned int *tile_order;
+	unsigned int       *tile_cost;
 };
 
 #endif

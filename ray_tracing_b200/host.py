@@ -143,6 +143,7 @@ EXPORTED_SYMBOLS = [
     "rt_cuda_debug_fp32_peak",
     "rt_cuda_debug_div_check",
     "rt_cuda_debug_set_sweep_threshold",
+    "rt_cuda_debug_set_tile_schedule",
     "rt_cuda_param_bytes",
     "rt_cuda_set_progressive",
     "rt_cuda_invalidate_accumulation",
@@ -211,6 +212,7 @@ def load_library() -> C.CDLL:
     L.rt_cuda_shared_frame_close.argtypes = [C.c_void_p, C.c_int]
     L.rt_cuda_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.rt_cuda_debug_set_sweep_threshold.argtypes = [C.c_float]
+    L.rt_cuda_debug_set_tile_schedule.argtypes = [C.c_int]
     L.rt_cuda_param_bytes.restype = C.c_size_t
     L.rt_cuda_set_progressive.argtypes = [C.c_int, C.c_int]
     L.rt_cuda_accum_generation.restype = C.c_uint32
@@ -552,6 +554,9 @@ class Renderer:
 
     def set_sweep_threshold(self, tau2: float) -> None:
         _check(self.lib.rt_cuda_debug_set_sweep_threshold(tau2))
+
+    def set_tile_schedule(self, on: bool) -> None:
+        _check(self.lib.rt_cuda_debug_set_tile_schedule(1 if on else 0))
 
     def fp32_peak_tflops(self, fma: bool = True) -> float:
         out = C.c_float()

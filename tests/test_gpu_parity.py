@@ -500,6 +500,44 @@ def test_4k_properties(renderer, port, real_sky, builtin_objects):
     assert a.min() >= 0.0 and a.max() <= 1.0
 
 
+def test_tile_schedule_changes_nothing(renderer, port, small_sky, builtin_objects):
+    """The queued kernel hands a pose's tiles out longest-first from the third
+    launch on (costs recorded by the second).  Scheduling only: every launch of the
+    sequence -- natural order, recording, reordered -- equals the oracle, with and
+    without interleaving, and leaves no pixel of a sentinel-filled frame behind."""
+    import torch
+
+    W, H = 640, 360                       # 7200 tiles: above the scheduling threshold
+    renderer.upload_skybox(small_sky)
+    renderer.upload_scene(builtin_objects[0])
+    want, rays = port.render(port.world(builtin_objects[0], small_sky), W, H, 1, 1, 0)
+    frame = torch.empty((H, W, 3), dtype=torch.float32, device="cuda")
+    try:
+        for on in (True, False, True):
+            renderer.set_tile_schedule(on)
+            for launch in range(4):
+                frame.fill_(-1.0)
+                st = renderer.render_into(Camera(), frame.data_ptr(), W, H, stats=True, scale=1, kernel=RT_KERNEL_QUEUED)
+                assert np.array_equal(bits(frame.cpu().numpy()), bits(want)), (on, launch)
+                assert st["rays"] == rays
+        # a different pass of the same pose reuses the order (costs barely move between passes)
+        want5, rays5 = port.render(port.world(builtin_objects[0], small_sky), W, H, 1, 1, 5)
+        frame.fill_(-1.0)
+        st = renderer.render_into(Camera(), frame.data_ptr(), W, H, stats=True, scale=1, pass_index=5, kernel=RT_KERNEL_QUEUED)
+        assert np.array_equal(bits(frame.cpu().numpy()), bits(want5)) and st["rays"] == rays5
+        # interleaved row blocks: each rank's launches build their own order
+        full = want
+        for rep in range(3):
+            frame.fill_(-1.0)
+            for rank in range(2):
+                renderer.render_into(Camera(), frame.data_ptr(), W, H, stats=True, scale=1, interleave_count=2, interleave_index=rank)
+                renderer.render_into(Camera(), frame.data_ptr(), W, H, stats=True, scale=1, interleave_count=2, interleave_index=rank)
+                renderer.render_into(Camera(), frame.data_ptr(), W, H, stats=True, scale=1, interleave_count=2, interleave_index=rank)
+            assert np.array_equal(bits(frame.cpu().numpy()), bits(full))
+    finally:
+        renderer.set_tile_schedule(True)
+
+
 # ------------------------------------------------------------------- LBVH
 
 

@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--reps", type=int, default=15)
     ap.add_argument("--tag", default="")
     ap.add_argument("--no-hash", action="store_true")
+    ap.add_argument("--no-schedule", action="store_true", help="queued kernel: keep tiles in image order")
+    ap.add_argument("--overlap", action="store_true", help="also time frames dealt to 1/2/3 streams")
     ap.add_argument("--one", action="store_true", help="render scene_0 4K with the first kernel a few times and exit (for ncu)")
     args = ap.parse_args()
     import torch
@@ -42,6 +44,8 @@ def main():
     r = host.Renderer(num_gpus=1)
     r.upload_skybox(faces)
     cam = host.Camera()
+    if args.no_schedule:
+        r.set_tile_schedule(False)
     frame = torch.zeros((2160, 3840, 3), dtype=torch.float32, device="cuda")
 
     if args.one:
@@ -50,6 +54,28 @@ def main():
             r.render_into(cam, frame.data_ptr(), 3840, 2160, stats=True, kernel=K[args.kernels.split(",")[0]])
         r.close()
         return
+
+    def overlapped(w, h, n, streams, **o):
+        """n frames back to back, dealt round robin to `streams` CUDA streams (two
+        frame buffers); returns ms per frame between events on the first stream."""
+        ss = [torch.cuda.Stream() for _ in range(streams)]
+        bufs = [torch.empty((h, w, 3), dtype=torch.float32, device="cuda") for _ in range(streams)]
+        best = 1e9
+        for rep in range(3):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(ss[0])
+            for s_ in ss[1:]:
+                s_.wait_event(e0)
+            for i in range(n):
+                k_ = i % streams
+                r.render_into(cam, bufs[k_].data_ptr(), w, h, stream=ss[k_].cuda_stream, **o)
+            for s_ in ss[1:]:
+                ss[0].wait_stream(s_)
+            e1.record(ss[0])
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) / n)
+        return round(best, 4), hashlib.sha256(bufs[-1].cpu().numpy().tobytes()).hexdigest()[:16]
 
     def sha(w, h):
         return hashlib.sha256(frame.view(-1)[: w * h * 3].cpu().numpy().tobytes()).hexdigest()[:16]
@@ -71,6 +97,11 @@ def main():
         for sc in (0, 1, 2):
             r.upload_scene(host.parse_scene_string(scenes.builtin_scene_text(sc)))
             if sc == 0:
+                if args.overlap:
+                    for nst in (1, 2, 3):
+                        out["time"]["ov%d_s0_4k" % nst] = overlapped(3840, 2160, 24, nst, kernel=k)
+                        out["time"]["ov%d_s0_4k_il8" % nst] = overlapped(3840, 2160, 48, nst, kernel=k, interleave_count=8, interleave_index=3)
+                        out["time"]["ov%d_s0_720p" % nst] = overlapped(1280, 720, 48, nst, kernel=k)
                 out["time"]["s0_4k"] = timed(3840, 2160, args.reps, kernel=k)
                 if not args.no_hash:
                     out["hash"]["s0_4k"] = sha(3840, 2160)
