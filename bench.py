@@ -190,7 +190,7 @@ def main_reference(args):
     try:
         r = reference_cpu_run(args.steps, args.warmup)
     except Exception as e:  # the oracle always exists; report rather than crash the driver
-        print(json.dumps({"impl": "reference", "unavailable": f"{type(e).__name__}: {e}"}))
+        print(json.dumps({"impl": "reference", "unavailable": f"{type(e).__name__}: {e}"}), file=args.out, flush=True)
         return 0
     line = {
         "impl": "reference", "metric": "Mrays/s", "value": r["mrays"], "unit": "Mrays/s", "n_gpus": args.gpus,
@@ -202,7 +202,7 @@ def main_reference(args):
         "e2e": {"value": r["mrays"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=args.out, flush=True)
     return 0
 
 
@@ -320,6 +320,27 @@ def main_gpu(args):
         dist.all_reduce(kern_ms, op=dist.ReduceOp.MAX)
     kern_ms = float(kern_ms.item())
 
+    # ---- the same launches with tiles in image order (what a pose costs the first two
+    # times it is rendered, and every time while the camera moves), for the record ----
+    unscheduled = None
+    if args.kernel in ("auto", "queued"):
+        r.set_tile_schedule(False)
+        for _ in range(3):
+            step_device()
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        u0.record()
+        for _ in range(10):
+            step_device()
+        u1.record()
+        barrier()
+        ums = torch.tensor([u0.elapsed_time(u1) / 10], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ums, op=dist.ReduceOp.MAX)
+        unscheduled = {"ms_per_step": float(ums.item()), "value": rays_per_step / (float(ums.item()) * 1e-3) / 1e6, "unit": "Mrays/s",
+                       "note": "tiles handed out in image order (no cost-sorted schedule)"}
+        r.set_tile_schedule(True)
+
     # ---- the other build of the same kernels, for the record (N=1 only) ----
     other = None
     if world == 1:
@@ -419,6 +440,7 @@ def main_gpu(args):
                 "framebuffer": "Vector3 f32x3 (reference frame format), bottom row first",
                 "l2": "no explicit flush: every step reads the 96 MiB RGBA8 skybox at random and writes a 99.5 MB frame (working set 196 MB > 126 MB L2)",
                 "rays_per_step": rays_per_step, "pixels_per_step": W * H,
+                "schedule": "every step renders the same pose, as the reference's progressive accumulation does (main.c:354-403); from the third launch of a pose the queued kernel hands out its 8x4 tiles longest-first, by the per-tile bounce counts the second launch recorded (warm-up). Scheduling only: frames are bit-identical. `unscheduled` = the same loop with tiles in image order",
             },
             "frames_per_s": 1e3 / per_step_ms,
             "e2e": {
@@ -448,6 +470,8 @@ def main_gpu(args):
         }
         if other:
             line["other_variant"] = other
+        if unscheduled:
+            line["unscheduled"] = unscheduled
         if world == 1 and not args.no_cpu_baseline:
             try:
                 c = reference_cpu_run(steps=1, warmup=0, budget_s=25.0)
@@ -455,7 +479,7 @@ def main_gpu(args):
                                         "sample": c["sample"], "host_cores": c["host_cores"], "frames_per_s": c["frames_per_s"]}
             except Exception as e:
                 line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "unavailable", "sample": f"{type(e).__name__}: {e}"}
-        print(json.dumps(line))
+        print(json.dumps(line), file=args.out, flush=True)
     if world > 1:
         dist.barrier()
         torch.cuda.cudart().cudaHostUnregister(host_addr)
@@ -479,6 +503,17 @@ def main_gpu(args):
     return 0
 
 
+def _claim_stdout():
+    """The driver reads ONE JSON line from stdout.  Libraries loaded later (NCCL
+    prints its version banner there when NCCL_DEBUG is set) must not add to it:
+    point fd 1 at stderr for the rest of the process and return a file on the real
+    stdout for the JSON line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -490,13 +525,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--composite", default="p2p", choices=["p2p", "nccl"], help="N>1: how bands reach rank 0")
     args = ap.parse_args()
-    if args.impl == "reference":
-        return main_reference(args)
-    if args.gpus > 1 and "RANK" not in os.environ:
+    if args.gpus > 1 and "RANK" not in os.environ and args.impl != "reference":
         # convenience: relaunch under torchrun, one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
+    args.out = _claim_stdout()
+    if args.impl == "reference":
+        return main_reference(args)
     return main_gpu(args)
 
 

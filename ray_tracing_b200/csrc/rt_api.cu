@@ -529,31 +529,47 @@ static int copy_owned_blocks(void *dst, const void *src, const PassPlan &pl, int
  * key, so frames are bit-identical with and without it (test_tile_schedule).
  */
 #define RT_ORDER_THREADS 512
+/* Stable counting sort of the tiles by descending cost class, one CTA: thread t
+ * owns a contiguous chunk (a multiple of 4 tiles, read as uint4; the cost array
+ * is padded with zeros to a multiple of 4). */
 __global__ void __launch_bounds__(RT_ORDER_THREADS) tile_order_kernel(const unsigned int *cost, unsigned int *order, unsigned n)
 {
 	__shared__ unsigned cnt[16][RT_ORDER_THREADS];
+	__shared__ unsigned total[16], base[16];
 	const unsigned t = threadIdx.x;
-	const unsigned chunk = (n + RT_ORDER_THREADS - 1) / RT_ORDER_THREADS;
-	const unsigned lo = min(t * chunk, n), hi = min(lo + chunk, n);
+	const unsigned chunk = (((n + RT_ORDER_THREADS - 1) / RT_ORDER_THREADS) + 3u) & ~3u;
+	const unsigned lo = min(t * chunk, (n + 3u) & ~3u), hi = min(lo + chunk, (n + 3u) & ~3u);
+	const uint4 *c4 = reinterpret_cast<const uint4 *>(cost);
 	for (int b = 0; b < 16; b++) cnt[b][t] = 0;
-	for (unsigned i = lo; i < hi; i++) cnt[min(cost[i], 15u)][t]++;
+#pragma unroll 4
+	for (unsigned i = lo; i < hi; i += 4) {
+		uint4 c = __ldg(c4 + (i >> 2));
+		cnt[min(c.x, 15u)][t]++;
+		if (i + 1 < n) cnt[min(c.y, 15u)][t]++;
+		if (i + 2 < n) cnt[min(c.z, 15u)][t]++;
+		if (i + 3 < n) cnt[min(c.w, 15u)][t]++;
+	}
 	__syncthreads();
 	/* exclusive scan over (class descending, thread ascending) */
-	__shared__ unsigned total[16];
 	if (t < 16) {
 		unsigned run = 0;
 		for (int k = 0; k < RT_ORDER_THREADS; k++) { unsigned c = cnt[t][k]; cnt[t][k] = run; run += c; }
 		total[t] = run;
 	}
 	__syncthreads();
-	unsigned base[16];
-	{
+	if (t == 0) {
 		unsigned run = 0;
 		for (int b = 15; b >= 0; b--) { base[b] = run; run += total[b]; }
 	}
-	for (unsigned i = lo; i < hi; i++) {
-		unsigned b = min(cost[i], 15u);
-		order[base[b] + cnt[b][t]++] = i;
+	__syncthreads();
+#pragma unroll 4
+	for (unsigned i = lo; i < hi; i += 4) {
+		uint4 c = __ldg(c4 + (i >> 2));
+		unsigned b;
+		b = min(c.x, 15u); order[base[b] + cnt[b][t]++] = i;
+		if (i + 1 < n) { b = min(c.y, 15u); order[base[b] + cnt[b][t]++] = i + 1; }
+		if (i + 2 < n) { b = min(c.z, 15u); order[base[b] + cnt[b][t]++] = i + 2; }
+		if (i + 3 < n) { b = min(c.w, 15u); order[base[b] + cnt[b][t]++] = i + 3; }
 	}
 }
 
@@ -573,7 +589,7 @@ static int tile_schedule(DeviceCtx &d, const TileKey &key, size_t tiles, RtRende
 		if (d.tile_capacity < tiles) {
 			cudaFree(d.tile_cost); cudaFree(d.tile_order);
 			d.tile_cost = d.tile_order = nullptr; d.tile_capacity = 0;
-			if (cudaMalloc(&d.tile_cost, tiles * sizeof(unsigned)) != cudaSuccess ||
+			if (cudaMalloc(&d.tile_cost, (tiles + 4) * sizeof(unsigned)) != cudaSuccess ||
 			    cudaMalloc(&d.tile_order, tiles * sizeof(unsigned)) != cudaSuccess) {
 				cudaGetLastError();
 				cudaFree(d.tile_cost); d.tile_cost = nullptr;
@@ -582,7 +598,7 @@ static int tile_schedule(DeviceCtx &d, const TileKey &key, size_t tiles, RtRende
 			d.tile_capacity = tiles;
 		}
 		if (!d.order_ready && cudaEventCreateWithFlags(&d.order_ready, cudaEventDisableTiming) != cudaSuccess) return 0;
-		if (cudaMemsetAsync(d.tile_cost, 0, tiles * sizeof(unsigned), stream) != cudaSuccess) return 0;
+		if (cudaMemsetAsync(d.tile_cost, 0, (tiles + 4) * sizeof(unsigned), stream) != cudaSuccess) return 0;
 		P.tile_cost = d.tile_cost;
 		return 1;
 	}

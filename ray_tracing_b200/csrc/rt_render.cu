@@ -395,6 +395,9 @@ __device__ __forceinline__ void rq_drain(const RtRenderParams &P, const SharedSc
 	else if (has) store_cell(P, c, color);
 }
 
+#ifndef RT_QUEUED_BATCH
+#define RT_QUEUED_BATCH RT_WARP_BATCH    /* most tiles per claim while tiles are in image order */
+#endif
 #ifndef RT_QUEUED_MIN_BLOCKS
 #define RT_QUEUED_MIN_BLOCKS 6
 #endif
@@ -469,7 +472,7 @@ render_queued_kernel(const __grid_constant__ RtRenderParams P)
 								unsigned seen = *(volatile unsigned *) P.work_counter;
 								unsigned left = seen < total ? (total - seen) >> 5 : 0;
 								unsigned warps = gridDim.x * (RT_BLOCK_THREADS / 32);
-								claim = min(max(left / (4u * warps), 1u), (unsigned) RT_WARP_BATCH) * 32u;
+								claim = min(max(left / (4u * warps), 1u), (unsigned) RT_QUEUED_BATCH) * 32u;
 							}
 							base = atomicAdd(P.work_counter, claim);
 						}

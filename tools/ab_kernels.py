@@ -50,7 +50,7 @@ def main():
 
     if args.one:
         r.upload_scene(host.parse_scene_string(scenes.builtin_scene_text(0)))
-        for _ in range(3):
+        for _ in range(5):      # launch 1 natural order, 2 records tile costs, 3.. scheduled
             r.render_into(cam, frame.data_ptr(), 3840, 2160, stats=True, kernel=K[args.kernels.split(",")[0]])
         r.close()
         return
