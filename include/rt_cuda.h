@@ -256,6 +256,24 @@ uint32_t rt_cuda_accum_generation(void);
 int      rt_cuda_update_frame(const RtCamera *cam, void *fb, int w, int h, double budget_ms,
                               const RtRenderOpts *opts, RtRenderStats *stats);
 
+/* CUDA-OpenGL interop presenter: replaces the per-frame host
+ * upload of move_frame_to_the_gpu() (gpu_and_windowing.c:371-376,
+ * glTexImage2D(GL_RGB, GL_FLOAT, host pointer)).  The application creates one
+ * GL_PIXEL_UNPACK_BUFFER of w*h*12 bytes (RT_FB_F32X3) or w*h*4 (RT_FB_U8X4) in
+ * the thread that owns the GL context and registers it once;
+ * rt_cuda_gl_update_frame() then maps the buffer, runs rt_cuda_update_frame()
+ * with the mapped device pointer as the frame and unmaps it, after which
+ * glTexImage2D(..., 0) with the buffer bound sources the texture from device
+ * memory: the frame never visits the host.  Must be called with the GL context
+ * current; fails with RT_ERR_CUDA (and the CUDA error text) when there is none.
+ * GL names are plain unsigned ints (GLuint); no GL header is needed here. */
+int rt_cuda_gl_register_buffer(unsigned int gl_buffer, size_t bytes);
+int rt_cuda_gl_update_frame(const RtCamera *cam, int w, int h, double budget_ms,
+                            const RtRenderOpts *opts, RtRenderStats *stats);
+/* same for a single explicit pass (render_frame_cuda_ex into the mapped buffer) */
+int rt_cuda_gl_render_frame(const RtCamera *cam, int w, int h, const RtRenderOpts *opts, RtRenderStats *stats);
+int rt_cuda_gl_unregister_buffer(void);
+
 /* Block until all work issued by the library has finished. */
 int rt_cuda_synchronize(void);
 

@@ -221,8 +221,11 @@ extern "C" int rt_cuda_init(int num_gpus)
 
 extern "C" int rt_cuda_init_device(int device) { return init_devices(&device, 1); }
 
+static void gl_release(void);      /* CUDA-OpenGL presenter, end of this file */
+
 extern "C" void rt_cuda_shutdown(void)
 {
+	gl_release();
 	for (int i = 0; i < g.ngpu; i++) free_device(g.dev[i]);
 	free(g.scene_cache);
 	g = Context();
@@ -1382,4 +1385,106 @@ extern "C" int rt_cuda_update_frame(const RtCamera *cam, void *fb, int w, int h,
 	}
 	if (stats) *stats = total;
 	return RT_OK;
+}
+
+/* ------------------------------------------------ CUDA-OpenGL presenter */
+
+/*
+ * the reference shows a frame with
+ *     glTexImage2D(GL_TEXTURE_2D, 0, GL_RGB, w, h, 0, GL_RGB, GL_FLOAT, data)
+ * from a host Vector3 array (gpu_and_windowing.c:371-376), i.e. a device->host
+ * copy here plus a host->device upload there per displayed frame.  With a
+ * registered pixel-unpack buffer the render kernels store straight into GL-owned
+ * device memory.  The two cudart entry points are declared here instead of
+ * including <cuda_gl_interop.h>, which wants a system GL header this library has
+ * no other use for (GLuint is `unsigned int` on every platform GL runs on).
+ */
+extern "C" cudaError_t cudaGraphicsGLRegisterBuffer(struct cudaGraphicsResource **resource, unsigned int buffer, unsigned int flags);
+
+static struct {
+	cudaGraphicsResource *res = nullptr;
+	size_t bytes = 0;
+} g_gl;
+
+static void gl_release(void)
+{
+	if (g_gl.res) { cudaGraphicsUnregisterResource(g_gl.res); cudaGetLastError(); }
+	g_gl.res = nullptr;
+	g_gl.bytes = 0;
+}
+
+extern "C" int rt_cuda_gl_register_buffer(unsigned int gl_buffer, size_t bytes)
+{
+	int rc = require_ready();
+	if (rc != RT_OK) return rc;
+	if (bytes == 0) return fail(RT_ERR_ARG, "GL buffer size must be given");
+	if (g.ngpu != 1) return fail(RT_ERR_ARG, "the GL presenter needs a single-GPU context (the GPU that owns the GL context)");
+	if ((rc = select_device(g.dev[0])) != RT_OK) return rc;
+	if (g_gl.res) { cudaGraphicsUnregisterResource(g_gl.res); g_gl.res = nullptr; }
+	cudaError_t e = cudaGraphicsGLRegisterBuffer(&g_gl.res, gl_buffer, cudaGraphicsRegisterFlagsWriteDiscard);
+	if (e != cudaSuccess) {
+		cudaGetLastError();
+		g_gl.res = nullptr;
+		return fail(RT_ERR_CUDA, "cudaGraphicsGLRegisterBuffer(%u): %s (is the GL context current on this thread?)", gl_buffer, cudaGetErrorString(e));
+	}
+	g_gl.bytes = bytes;
+	return RT_OK;
+}
+
+extern "C" int rt_cuda_gl_unregister_buffer(void)
+{
+	if (!g_gl.res) return RT_OK;
+	cudaError_t e = cudaGraphicsUnregisterResource(g_gl.res);
+	g_gl.res = nullptr;
+	g_gl.bytes = 0;
+	if (e != cudaSuccess) { cudaGetLastError(); return fail(RT_ERR_CUDA, "cudaGraphicsUnregisterResource: %s", cudaGetErrorString(e)); }
+	return RT_OK;
+}
+
+/* map -> fn(device pointer) -> unmap, on the library stream */
+template <class Fn>
+static int with_mapped_gl_buffer(int w, int h, const RtRenderOpts *opts, Fn fn)
+{
+	int rc = require_ready();
+	if (rc != RT_OK) return rc;
+	if (!g_gl.res) return fail(RT_ERR_STATE, "no GL buffer registered (rt_cuda_gl_register_buffer)");
+	if (w <= 0 || h <= 0) return fail(RT_ERR_ARG, "bad frame size %dx%d", w, h);
+	RtRenderOpts o;
+	if (opts) o = *opts; else rt_render_opts_default(&o);
+	if (o.struct_size != sizeof(RtRenderOpts)) return fail(RT_ERR_ARG, "opts->struct_size mismatch (ABI)");
+	if ((rc = select_device(g.dev[0])) != RT_OK) return rc;
+	cudaStream_t st = o.stream ? (cudaStream_t) o.stream : g.dev[0].stream;
+	CU(cudaGraphicsMapResources(1, &g_gl.res, st));
+	void *ptr = nullptr;
+	size_t mapped = 0;
+	cudaError_t e = cudaGraphicsResourceGetMappedPointer(&ptr, &mapped, g_gl.res);
+	size_t need = (size_t) w * h * bytes_per_pixel(o.fb_format);
+	if (e != cudaSuccess || mapped < need) {
+		cudaGetLastError();
+		cudaGraphicsUnmapResources(1, &g_gl.res, st);
+		if (e != cudaSuccess) return fail(RT_ERR_CUDA, "cudaGraphicsResourceGetMappedPointer: %s", cudaGetErrorString(e));
+		return fail(RT_ERR_ARG, "the registered GL buffer holds %zu bytes, a %dx%d frame needs %zu", mapped, w, h, need);
+	}
+	o.fb_memory = RT_MEM_DEVICE;
+	rc = fn(ptr, &o);
+	/* unmapping orders the GL commands that follow after the work on `st` */
+	cudaError_t u = cudaGraphicsUnmapResources(1, &g_gl.res, st);
+	if (rc != RT_OK) return rc;
+	if (u != cudaSuccess) { cudaGetLastError(); return fail(RT_ERR_CUDA, "cudaGraphicsUnmapResources: %s", cudaGetErrorString(u)); }
+	return RT_OK;
+}
+
+extern "C" int rt_cuda_gl_update_frame(const RtCamera *cam, int w, int h, double budget_ms,
+                                       const RtRenderOpts *opts, RtRenderStats *stats)
+{
+	return with_mapped_gl_buffer(w, h, opts, [&](void *ptr, const RtRenderOpts *o) {
+		return rt_cuda_update_frame(cam, ptr, w, h, budget_ms, o, stats);
+	});
+}
+
+extern "C" int rt_cuda_gl_render_frame(const RtCamera *cam, int w, int h, const RtRenderOpts *opts, RtRenderStats *stats)
+{
+	return with_mapped_gl_buffer(w, h, opts, [&](void *ptr, const RtRenderOpts *o) {
+		return render_frame_cuda_ex(cam, ptr, w, h, o, stats);
+	});
 }

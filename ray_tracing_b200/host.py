@@ -153,6 +153,10 @@ EXPORTED_SYMBOLS = [
     "rt_cuda_shared_frame_open",
     "rt_cuda_shared_frame_close",
     "rt_cuda_copy_to_host",
+    "rt_cuda_gl_register_buffer",
+    "rt_cuda_gl_update_frame",
+    "rt_cuda_gl_render_frame",
+    "rt_cuda_gl_unregister_buffer",
 ]
 
 _lib = None
@@ -213,6 +217,9 @@ def load_library() -> C.CDLL:
     L.rt_cuda_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.rt_cuda_debug_set_sweep_threshold.argtypes = [C.c_float]
     L.rt_cuda_debug_set_tile_schedule.argtypes = [C.c_int]
+    L.rt_cuda_gl_register_buffer.argtypes = [C.c_uint, C.c_size_t]
+    L.rt_cuda_gl_update_frame.argtypes = [C.POINTER(RtCamera), C.c_int, C.c_int, C.c_double, C.POINTER(RtRenderOpts), C.POINTER(RtRenderStats)]
+    L.rt_cuda_gl_render_frame.argtypes = [C.POINTER(RtCamera), C.c_int, C.c_int, C.POINTER(RtRenderOpts), C.POINTER(RtRenderStats)]
     L.rt_cuda_param_bytes.restype = C.c_size_t
     L.rt_cuda_set_progressive.argtypes = [C.c_int, C.c_int]
     L.rt_cuda_accum_generation.restype = C.c_uint32
@@ -554,6 +561,20 @@ class Renderer:
 
     def set_sweep_threshold(self, tau2: float) -> None:
         _check(self.lib.rt_cuda_debug_set_sweep_threshold(tau2))
+
+    # -- CUDA-OpenGL presenter (needs a current GL context)
+    def gl_register_buffer(self, gl_buffer: int, nbytes: int) -> None:
+        _check(self.lib.rt_cuda_gl_register_buffer(gl_buffer, nbytes))
+
+    def gl_update_frame(self, camera: Camera, w: int, h: int, budget_ms: float = 0.0, **opts):
+        o = self._opts(**opts)
+        st = RtRenderStats()
+        cam = camera.as_struct()
+        _check(self.lib.rt_cuda_gl_update_frame(C.byref(cam), w, h, budget_ms, C.byref(o), C.byref(st)))
+        return _stats_dict(st)
+
+    def gl_unregister_buffer(self) -> None:
+        _check(self.lib.rt_cuda_gl_unregister_buffer())
 
     def set_tile_schedule(self, on: bool) -> None:
         _check(self.lib.rt_cuda_debug_set_tile_schedule(1 if on else 0))

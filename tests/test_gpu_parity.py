@@ -538,6 +538,23 @@ def test_tile_schedule_changes_nothing(renderer, port, small_sky, builtin_object
         renderer.set_tile_schedule(True)
 
 
+def test_gl_presenter_fails_loudly_without_a_gl_context(renderer, small_sky, builtin_objects):
+    """SURVEY N3: the CUDA-OpenGL presenter cannot be exercised on a headless box;
+    what can be is that it reports the missing GL context / buffer as an error
+    instead of crashing or silently rendering somewhere else."""
+    renderer.upload_skybox(small_sky)
+    renderer.upload_scene(builtin_objects[0])
+    with pytest.raises(host.RtError) as e:
+        renderer.gl_update_frame(Camera(), 160, 90)          # nothing registered
+    assert "registered" in str(e.value)
+    with pytest.raises(host.RtError) as e:
+        renderer.gl_register_buffer(1, 160 * 90 * 12)        # no GL context on this thread
+    assert "cudaGraphicsGLRegisterBuffer" in str(e.value)
+    renderer.gl_unregister_buffer()                          # a no-op, not an error
+    frame, st = renderer.render_frame(Camera(), 160, 90, 1)  # the library is still usable
+    assert st["rays"] > 0
+
+
 # ------------------------------------------------------------------- LBVH
 
 
