@@ -23,13 +23,13 @@ def main():
     ap.add_argument("--variant", default="exact")
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--skip-100k", action="store_true")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "pixel", "persistent", "wavefront"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "pixel", "persistent", "wavefront", "queued"])
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     import torch
 
     variant = host.RT_VARIANT_FAST if a.variant == "fast" else host.RT_VARIANT_EXACT
-    kern = {"auto": 0, "pixel": 1, "persistent": 2, "wavefront": 3}[a.kernel]
+    kern = {"auto": 0, "pixel": 1, "persistent": 2, "wavefront": 3, "queued": 4}[a.kernel]
     faces, sky_desc = bench.load_skybox_faces()
     r = host.Renderer(num_gpus=1)
     r.upload_skybox(faces)
@@ -42,6 +42,8 @@ def main():
         for _ in range(a.reps):
             st = r.render_into(cam, frame.data_ptr(), w, h, stats=True, variant=variant, kernel=kern, **kw)
             best = min(best, st["render_ms"])
+        # the same pose is launched a.reps times: from the third launch on the queued kernel
+        # (linear-scan scenes of >= 2048 tiles) hands tiles out longest-first; `ms` is the best launch
         rec = dict(config=label, w=w, h=h, ms=best, rays=st["rays"], mrays_s=st["rays"] / best / 1e3, fps=1e3 / best, **{k: v for k, v in kw.items() if k in ("scale", "traversal")})
         out.append(rec)
         print(json.dumps(rec))
