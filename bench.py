@@ -443,6 +443,7 @@ def main_gpu(args):
                 "schedule": "every step renders the same pose, as the reference's progressive accumulation does (main.c:354-403); from the third launch of a pose the queued kernel hands out its 8x4 tiles longest-first, by the per-tile bounce counts the second launch recorded (warm-up). Scheduling only: frames are bit-identical. `unscheduled` = the same loop with tiles in image order",
             },
             "frames_per_s": 1e3 / per_step_ms,
+            "mpix_per_s": W * H / (per_step_ms * 1e-3) / 1e6,
             "e2e": {
                 "value": rays_per_step * e2e_steps / e2e_s / 1e6, "unit": "Mrays/s",
                 "h2d_bytes_per_step": int(host.load_library().rt_cuda_param_bytes()) * world,   # kernel-argument block (camera frame, views, sizes) per rank; scene and skybox are resident
