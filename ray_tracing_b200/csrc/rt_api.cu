@@ -101,6 +101,7 @@ struct DeviceCtx {
 	size_t        tile_capacity = 0;
 	TileKey       order_key;
 	int           order_state = 0;                        /* 0 none, 1 key seen once, 2 order built */
+	bool          order_in_use = false;                   /* tile_order was given to a launch since it was allocated */
 	cudaEvent_t   order_ready = nullptr;
 	/* pipelined host read-back: two staging frames + a copy stream */
 	cudaStream_t copy_stream = nullptr;
@@ -146,7 +147,7 @@ static void free_device(DeviceCtx &d)
 	cudaFree(d.fb); cudaFree(d.accum);
 	cudaFree(d.ray_counter); cudaFree(d.work_counter);
 	cudaFree(d.tile_cost); cudaFree(d.tile_order);
-	d.tile_cost = d.tile_order = nullptr; d.tile_capacity = 0; d.order_state = 0;
+	d.tile_cost = d.tile_order = nullptr; d.tile_capacity = 0; d.order_state = 0; d.order_in_use = false;
 	if (d.order_ready) { cudaEventDestroy(d.order_ready); d.order_ready = nullptr; }
 	if (d.host_rays) cudaFreeHost(d.host_rays);
 	for (auto &e : d.ev) if (e) cudaEventDestroy(e);
@@ -589,7 +590,11 @@ static int tile_schedule(DeviceCtx &d, const TileKey &key, size_t tiles, RtRende
 		return 0;
 	}
 	if (d.order_state == 1) {
-		if (d.tile_capacity < tiles) {
+		/* An order that was handed to earlier launches may still be read by one of
+		 * them on another caller stream: never overwrite it.  cudaFree() waits for
+		 * all work on the device, then fresh buffers are used. */
+		if (d.tile_capacity < tiles || d.order_in_use) {
+			d.order_in_use = false;
 			cudaFree(d.tile_cost); cudaFree(d.tile_order);
 			d.tile_cost = d.tile_order = nullptr; d.tile_capacity = 0;
 			if (cudaMalloc(&d.tile_cost, (tiles + 4) * sizeof(unsigned)) != cudaSuccess ||
@@ -607,6 +612,7 @@ static int tile_schedule(DeviceCtx &d, const TileKey &key, size_t tiles, RtRende
 	}
 	cudaStreamWaitEvent(stream, d.order_ready, 0);     /* the order may have been built on another stream */
 	P.tile_order = d.tile_order;
+	d.order_in_use = true;
 	return 2;
 }
 
