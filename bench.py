@@ -188,7 +188,8 @@ def main_reference(args):
     if rank != 0:
         return 0
     try:
-        r = reference_cpu_run(args.steps, args.warmup)
+        # RT_BENCH_REF_BUDGET_S bounds the CPU time of the whole run (tests use a few seconds)
+        r = reference_cpu_run(args.steps, args.warmup, budget_s=float(os.environ.get("RT_BENCH_REF_BUDGET_S", "150")))
     except Exception as e:  # the oracle always exists; report rather than crash the driver
         print(json.dumps({"impl": "reference", "unavailable": f"{type(e).__name__}: {e}"}), file=args.out, flush=True)
         return 0
