@@ -1038,7 +1038,7 @@ extern "C" int rt_cuda_debug_trace(const float *rays6, int n, float *out7, int32
 	int rc = require_ready();
 	if (rc != RT_OK) return rc;
 	if (!g.have_scene) return fail(RT_ERR_STATE, "no scene uploaded");
-	bool lbvh;
+	bool lbvh = false;
 	if ((rc = pick_traversal(traversal, &lbvh)) != RT_OK) return rc;
 	DeviceCtx &d = g.dev[0];
 	if ((rc = select_device(d)) != RT_OK) return rc;
