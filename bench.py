@@ -247,8 +247,8 @@ def main_gpu(args):
     p2p = world > 1 and args.composite == "p2p"
     shared_ptr = None
     if p2p:
-        # fused composite: every rank's render kernel stores its band straight into
-        # rank 0's frame through a peer mapping (cudaIpc), no gather collective
+        # composite without a data-path collective: every rank renders its row blocks locally and
+        # ships them with one strided peer copy into rank 0's frame (cudaIpc mapping)
         box = [None]
         if rank == 0:
             shared_ptr, handle = r.shared_frame_create(W * H * 12)

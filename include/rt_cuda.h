@@ -234,10 +234,13 @@ float rt_cuda_accum_count(void);
 int rt_cuda_render_sweep(const RtCamera *cam, void *fb, int w, int h, int init_scale,
                          uint64_t first_pass, const RtRenderOpts *opts, RtRenderStats *stats);
 
-/* One-process-per-GPU composite over NVLink without a collective: rank 0
- * creates the frame and shares the 64-byte handle; the other ranks open it and
- * render their row band straight into it (peer stores from the kernel
- * epilogue).  close: owner = 1 on the creating rank, 0 elsewhere. */
+/* One-process-per-GPU composite over NVLink without a data-path collective:
+ * rank 0 creates the frame and shares the 64-byte handle; the other ranks open
+ * it and pass the mapped address as `fb` with opts->interleave_* and
+ * opts->remote_fb = 1: they render the row blocks they own into local memory
+ * and ship them with one strided peer copy into the shared frame (direct peer
+ * stores from the kernel were measured first: small scattered writes over
+ * NVLink, slower).  close: owner = 1 on the creating rank, 0 elsewhere. */
 int rt_cuda_shared_frame_create(size_t bytes, void **dev_ptr, void *handle64);
 int rt_cuda_shared_frame_open(const void *handle64, void **dev_ptr);
 int rt_cuda_shared_frame_close(void *dev_ptr, int owner);

@@ -1210,8 +1210,9 @@ extern "C" int rt_cuda_debug_div_check(uint64_t seed, unsigned blocks, unsigned 
  * frame with rt_cuda_shared_frame_create() and hands the 64-byte handle to the
  * other ranks (any transport; bench.py uses torch.distributed); they map it
  * with rt_cuda_shared_frame_open() and pass the mapped address as `fb` with
- * their row band, so the render kernel's epilogue stores the band straight
- * into GPU 0's memory over NVLink (peer stores; SURVEY.md 8(e) option (a)).
+ * their interleave index and remote_fb = 1: each rank renders the row blocks it
+ * owns locally and copy_owned_blocks() ships them into GPU 0's memory over
+ * NVLink with one strided peer copy.
  */
 extern "C" int rt_cuda_shared_frame_create(size_t bytes, void **dev_ptr, void *handle64)
 {
