@@ -9,7 +9,8 @@ One *step* = one full pass of the hot path over one frame:
     skybox (6 x 2048^2) -- BASELINE.json configs[2], the configuration its
     metric names for 1/2/4/8 B200; the same workload at every N so the
     driver's scaling numbers compare like with like (N=1 renders the whole
-    frame, N>1 row bands of H/N rows composited to rank 0: strong scaling).
+    frame, N>1 the rows in 16-row blocks dealt round robin and composited to
+    rank 0: strong scaling).
 Metric: Mrays/s = trace_ray-equivalent invocations (primary + bounce + shadow
 rays, counted by the kernel that traced them) per second, whole job.
 
@@ -39,7 +40,7 @@ if ROOT not in sys.path:
 W, H = 3840, 2160
 SCENE = 0
 FLOPS_PER_RAY = {0: 141, 1: 105, 2: 69}     # 15 + 18*spheres + 12*cubes
-WORKLOAD = "scene_0.txt 3840x2160 scale 1, default pose, pass 0 (BASELINE.json configs[2]); N>1: row bands of H/N rows composited to rank 0"
+WORKLOAD = "scene_0.txt 3840x2160 scale 1, default pose, pass 0 (BASELINE.json configs[2]); N>1: the frame's rows dealt to the ranks in 16-row blocks, round robin, composited to rank 0"
 STAGED = os.path.join(ROOT, "oracle", "_ref", "assets")
 
 
