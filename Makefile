@@ -18,7 +18,7 @@ CFLAGS    := -std=c11 -O2 -fPIC -ffp-contract=off -Wall -Wextra -Iinclude -I$(SR
 
 HOST_OBJS := $(OBJ)/scene_parse.o $(OBJ)/camera_host.o $(OBJ)/scene_pack.o $(OBJ)/screenshot.o
 CUDA_OBJS := $(OBJ)/rt_api.o $(OBJ)/rt_lbvh.o $(OBJ)/rt_render_exact.o $(OBJ)/rt_render_fast.o
-DEVICE_HDRS := $(SRC)/rt_device.cuh $(SRC)/rt_params.h $(SRC)/rt_host.h $(SRC)/rt_lbvh.h include/rt_cuda.h
+DEVICE_HDRS := $(SRC)/rt_device.cuh $(SRC)/rt_params.h $(SRC)/rt_host.h $(SRC)/rt_lbvh.h $(SRC)/rt_lbvh_rule.h include/rt_cuda.h
 
 .PHONY: all oracle harness clean
 all: $(LIB) $(HARNESS)

@@ -2,21 +2,13 @@
  * rt_lbvh.cu -- device LBVH build (Morton codes -> radix sort -> Karras 2012
  * hierarchy -> bottom-up refit) for scenes above RT_LBVH_THRESHOLD objects.
  *
- * Parity contract: traversal (rt_device.cuh: nearest_lbvh) must return what
- * the reference's linear scan (scene.c:156-173) returns, bit for bit.  The
+ * Parity contract: traversal (rt_device.cuh: walk_nodes / walk_leaf) must return
+ * what the reference's linear scan (scene.c:156-173) returns, bit for bit.  The
  * per-primitive arithmetic is the same device function as the linear scan, and
  * ties go to the lower primitive index; what the hierarchy must guarantee is
- * that no primitive the reference would accept is ever culled.  The
- * reference's sphere test is "fuzzy": c = oc.oc - r*r and discr = b*b - 4ac
- * cancel in binary32 when the origin-centre distance D >> r, so it reports
- * hits for rays that geometrically miss by m with m^2 <= r^2 + k*2^-24*D^2
- * (measured k <= 5.6; a first-order error bound of the
- * binary32 evaluation gives k ~ 15).  Boxes therefore bound the sphere of
- * radius sqrt(r^2 + K*2^-24*D_max^2), K = 32, where D_max is the largest
- * distance from any ray origin (camera or a surface point) to any primitive;
- * cubes get a few-ulp pad, and a node is culled only when its entry distance
- * exceeds best + t_slack (1e-3 * D_max), which also keeps equal-t candidates
- * alive for the index tie-break.
+ * that no primitive the reference would accept is ever culled.  The padding
+ * rule that guarantees it, and why, is stated once in rt_lbvh_rule.h and
+ * checked on the CPU against the O(N) scan by tests/lbvh_sim.c.
  */
 #include <cub/device/device_radix_sort.cuh>
 
@@ -25,6 +17,7 @@
 #include <stdio.h>
 
 #include "rt_lbvh.h"
+#include "rt_lbvh_rule.h"
 #include "rt_cuda.h"
 
 static thread_local char lbvh_err[256] = "";
@@ -46,9 +39,8 @@ static int lfail(int code, const char *fmt, ...)
 			return lfail(RT_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_));                    \
 	} while (0)
 
-#define RT_FUZZ_K 32.0
-static double g_fuzz_k = RT_FUZZ_K;
-static double g_slack = 1e-3;
+static double g_fuzz_k = RT_LBVH_FUZZ_K;
+static double g_slack = RT_LBVH_SLACK;
 extern "C" void rt_lbvh_debug_set(double k, double slack) { g_fuzz_k = k; g_slack = slack; }
 
 /* ---- Morton keys -------------------------------------------------------- */
@@ -82,10 +74,16 @@ __global__ void morton_kernel(const float4 *A, const float4 *B, int n, float3 lo
 	keys[i] = ((unsigned long long) code << 32) | (unsigned int) i;
 }
 
-__global__ void unpack_index_kernel(const unsigned long long *keys, int n, int *prim_index)
+/* sorted keys -> primitive index per leaf slot, and the primitive records in that order */
+__global__ void unpack_index_kernel(const unsigned long long *keys, int n, const float4 *A, const float4 *B,
+                                    int *prim_index, float4 *leafA, float4 *leafB)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n) prim_index[i] = (int) (unsigned int) (keys[i] & 0xffffffffull);
+	if (i >= n) return;
+	int p = (int) (unsigned int) (keys[i] & 0xffffffffull);
+	prim_index[i] = p;
+	leafA[i] = A[p];
+	leafB[i] = B[p];
 }
 
 /* ---- Karras hierarchy ---------------------------------------------------- */
@@ -125,6 +123,16 @@ __global__ void hierarchy_kernel(const unsigned long long *keys, int n, int *chi
 	parent[left >= 0 ? left : (n - 1) + ~left] = i;
 	parent[right >= 0 ? right : (n - 1) + ~right] = i;
 	if (i == 0) parent[0] = -1;
+}
+
+/* deepest leaf: what a near-first walk can have on its stack at most */
+__global__ void depth_kernel(const int *parent, int n, int *depth_out)
+{
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= n) return;
+	int d = 0;
+	for (int cur = parent[(n - 1) + s]; cur >= 0; cur = parent[cur]) d++;
+	atomicMax(depth_out, d);
 }
 
 /* ---- padded leaf boxes ---------------------------------------------------- */
@@ -211,6 +219,7 @@ void rt_lbvh_free(RtLbvh *bvh)
 {
 	cudaFree(bvh->nodes); cudaFree(bvh->prim_index); cudaFree(bvh->parent);
 	cudaFree(bvh->leaf_lo); cudaFree(bvh->leaf_hi); cudaFree(bvh->visit);
+	cudaFree(bvh->leafA); cudaFree(bvh->leafB);
 	*bvh = RtLbvh();
 }
 
@@ -219,7 +228,10 @@ RtBvhView rt_lbvh_view(const RtLbvh *bvh)
 	RtBvhView v;
 	v.nodes = bvh->nodes;
 	v.prim_index = bvh->prim_index;
+	v.leafA = bvh->leafA;
+	v.leafB = bvh->leafB;
 	v.num_prims = bvh->num_prims;
+	v.depth = bvh->depth;
 	v.t_slack = bvh->t_slack;
 	return v;
 }
@@ -236,15 +248,12 @@ int rt_lbvh_refit(RtLbvh *bvh, const float4 *geomA, const float4 *geomB, float d
 {
 	int n = bvh->num_prims;
 	if (n <= 0) return RT_OK;
-	double D = (double) d_max;
-	double fuzz_r2 = g_fuzz_k * ldexp(1.0, -24) * D * D;
 	double mag = fmax(fmax(fabs((double) bvh->lo.x), fabs((double) bvh->hi.x)),
 	                  fmax(fmax(fabs((double) bvh->lo.y), fabs((double) bvh->hi.y)),
 	                       fmax(fabs((double) bvh->lo.z), fabs((double) bvh->hi.z))));
-	float cube_pad = (float) (ldexp(1.0, -20) * (mag + D));
-	float extra = (float) (ldexp(1.0, -18) * (mag + D));
+	RtLbvhPads pads = rt_lbvh_pads(mag, (double) d_max, g_fuzz_k, g_slack);
 	int blocks = (n + 255) / 256;
-	leaf_box_kernel<<<blocks, 256, 0, stream>>>(geomA, geomB, bvh->prim_index, n, fuzz_r2, cube_pad, extra,
+	leaf_box_kernel<<<blocks, 256, 0, stream>>>(geomA, geomB, bvh->prim_index, n, pads.fuzz_r2, pads.cube_pad, pads.extra,
 	                                            bvh->leaf_lo, bvh->leaf_hi);
 	LCU(cudaGetLastError());
 	if (n >= 2) {
@@ -257,7 +266,7 @@ int rt_lbvh_refit(RtLbvh *bvh, const float4 *geomA, const float4 *geomB, float d
 		LCU(cudaStreamSynchronize(stream));
 	}
 	bvh->d_max = d_max;
-	bvh->t_slack = (float) (g_slack * D);
+	bvh->t_slack = pads.t_slack;
 	return RT_OK;
 }
 
@@ -277,6 +286,8 @@ int rt_lbvh_build(RtLbvh *bvh, const float4 *geomA, const float4 *geomB, int n,
 	LCU(cudaMalloc(&bvh->leaf_lo, sizeof(float4) * nn));
 	LCU(cudaMalloc(&bvh->leaf_hi, sizeof(float4) * nn));
 	LCU(cudaMalloc(&bvh->visit, sizeof(unsigned int) * (nn > 1 ? nn - 1 : 1)));
+	LCU(cudaMalloc(&bvh->leafA, sizeof(float4) * nn));
+	LCU(cudaMalloc(&bvh->leafB, sizeof(float4) * nn));
 
 	Scratch keys_in, keys_out, temp;
 	LCU(cudaMalloc(&keys_in.p, sizeof(unsigned long long) * nn));
@@ -296,19 +307,26 @@ int rt_lbvh_build(RtLbvh *bvh, const float4 *geomA, const float4 *geomB, int n,
 	LCU(cudaMalloc(&temp.p, temp_bytes ? temp_bytes : 4));
 	LCU(cub::DeviceRadixSort::SortKeys(temp.p, temp_bytes, (const unsigned long long *) keys_in.p,
 	                                   (unsigned long long *) keys_out.p, n, 0, 64, stream));
-	unpack_index_kernel<<<blocks, 256, 0, stream>>>((const unsigned long long *) keys_out.p, n, bvh->prim_index);
+	unpack_index_kernel<<<blocks, 256, 0, stream>>>((const unsigned long long *) keys_out.p, n, geomA, geomB,
+	                                                bvh->prim_index, bvh->leafA, bvh->leafB);
 	LCU(cudaGetLastError());
 	if (n >= 2) {
 		hierarchy_kernel<<<blocks, 256, 0, stream>>>((const unsigned long long *) keys_out.p, n,
 		                                             g_children_of(bvh), bvh->parent);
 		LCU(cudaGetLastError());
 	}
+	if (n >= 2) {
+		/* visit[0] doubles as the result cell (refit clears the array afterwards) */
+		LCU(cudaMemsetAsync(bvh->visit, 0, sizeof(unsigned int), stream));
+		depth_kernel<<<blocks, 256, 0, stream>>>(bvh->parent, n, (int *) bvh->visit);
+		LCU(cudaGetLastError());
+		LCU(cudaMemcpyAsync(&bvh->depth, bvh->visit, sizeof(int), cudaMemcpyDeviceToHost, stream));
+	}
 	LCU(cudaStreamSynchronize(stream));
 
 	/* secondary rays start on surfaces, i.e. inside the primitive bounds: their
 	 * distance to any primitive is at most the bounds' diagonal.  The renderer
 	 * re-pads when the camera is farther than that (rt_api.cu). */
-	double dx = (double) ext.x, dy = (double) ext.y, dz = (double) ext.z;
-	float d_max = (float) (1.01 * sqrt(dx * dx + dy * dy + dz * dz) + 0.01);
+	float d_max = rt_lbvh_default_dmax((double) ext.x, (double) ext.y, (double) ext.z);
 	return rt_lbvh_refit(bvh, geomA, geomB, d_max, stream);
 }

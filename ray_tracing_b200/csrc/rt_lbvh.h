@@ -17,8 +17,10 @@ struct RtLbvh {
 	int    *prim_index = nullptr;   /* Morton order -> primitive index */
 	int    *parent = nullptr;       /* internal-node parents; leaves at [n-1, 2n-1) */
 	float4 *leaf_lo = nullptr, *leaf_hi = nullptr;   /* padded primitive boxes, Morton order */
+	float4 *leafA = nullptr, *leafB = nullptr;       /* geomA / geomB records, Morton order (one load chain fewer per leaf) */
 	unsigned int *visit = nullptr;
 	int     num_prims = 0;
+	int     depth = 0;              /* deepest leaf, in levels below the root */
 	float   d_max = 0.0f;           /* largest origin-to-primitive distance the padding covers */
 	float   t_slack = 0.0f;
 	RtVector3 lo = {0, 0, 0}, hi = {0, 0, 0};   /* unpadded bounds of all primitives */

@@ -10,6 +10,9 @@
 #include "rt_host.h"
 
 #define RT_BVH_STACK 64
+#ifndef RT_SMEM_STACK
+#define RT_SMEM_STACK 32         /* traversal-stack entries per thread in shared memory (config 5: depth 13 used); deeper trees use the local-memory build */
+#endif
 #define RT_TILE_W 8           /* a warp covers an 8x4 tile of low-res pixels */
 #define RT_TILE_H 4
 #define RT_BLOCK_THREADS 128
@@ -45,7 +48,9 @@ struct RtSkyView {
 struct RtBvhView {
 	const float4 *nodes;
 	const int    *prim_index;
+	const float4 *leafA, *leafB;  /* geomA / geomB in Morton order (leaf slot -> record) */
 	int           num_prims;
+	int           depth;      /* deepest leaf (levels below the root) = most stack entries a walk can hold */
 	float         t_slack;    /* see rt_lbvh.cu: cull only if t_entry > best + slack */
 };
 

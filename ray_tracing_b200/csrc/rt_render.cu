@@ -20,6 +20,8 @@
  * (every lane reads the same primitive: broadcast, no bank conflicts); larger
  * ones walk the LBVH in global memory.
  */
+#include <type_traits>
+
 #include "rt_device.cuh"
 
 namespace RT_NS {
@@ -32,6 +34,7 @@ struct SharedScene {
 	float  *lut;
 	unsigned char *sweep;     /* 32 bytes per warp: lane list of warp_sweep() */
 	int2   *runs;             /* type runs of the scene (rt_device.cuh: nearest_linear) */
+	int    *stack;            /* LBVH: this thread's traversal-stack column (rt_device.cuh: SharedStack) */
 };
 
 /* `smem` = start of the scene area: kernels that keep per-warp queues in shared
@@ -44,6 +47,7 @@ __device__ __forceinline__ SharedScene stage_scene(const RtRenderParams &P, unsi
 	s.sweep = smem + 256 * sizeof(float) + 32 * (threadIdx.x >> 5);
 	s.A = reinterpret_cast<float4 *>(smem + 256 * sizeof(float) + RT_BLOCK_THREADS);
 	s.B = s.A + 1;            /* records interleaved: A[2*i], B[2*i] are neighbours (one address per object) */
+	s.stack = reinterpret_cast<int *>(s.A) + threadIdx.x;   /* LBVH scenes stage no objects: the area holds the stacks */
 	s.runs = reinterpret_cast<int2 *>(s.A + (linear ? 2 * P.scene.n : 0));
 	for (int i = threadIdx.x; i < 256; i += blockDim.x) s.lut[i] = __ldg(&P.byte_lut[i]);
 	if (linear)
@@ -191,30 +195,73 @@ __device__ __forceinline__ void count_rays(const RtRenderParams &P, unsigned ray
 	if ((threadIdx.x & 31) == 0 && rays) atomicAdd(P.ray_counter, (unsigned long long) rays);
 }
 
+__device__ __forceinline__ void stack_init(SharedStack &st, const SharedScene &S) { st.col = S.stack; }
+__device__ __forceinline__ void stack_init(LocalStack &, const SharedScene &) {}
+
 /*
  * One warp step: every lane with a pending ray traces it and consumes the hit
  * (classify), the warp shares out the light-sample tests of the new surfaces
  * (sweep), then every lane that still has a surface to work on builds its next
  * ray (launch).  Must be called by all 32 lanes.  Returns 1 for lanes that
- * traced a ray.
+ * started a ray.
+ *
+ * LBVH scenes: a ray's walk (rt_device.cuh: Walk) is spread over as many warp
+ * steps as it needs.  One step = up to RT_WALK_ITERS internal nodes per lane,
+ * then -- the warp reconverged in between -- the parked leaves, then the sphere
+ * roots.  Lanes whose walk ended wait (MODE_HIT) until RT_WALK_HOLD of them do, or
+ * nobody walks any more, so that classify / sweep / launch run with a fuller warp.
  */
-template <bool LBVH, bool DEFER_SKY = false>
-__device__ __forceinline__ unsigned warp_step(Path &p, const RtRenderParams &P, const SharedScene &S)
+#ifndef RT_WALK_ITERS
+#define RT_WALK_ITERS 8
+#endif
+#ifndef RT_WALK_HOLD
+#define RT_WALK_HOLD 8
+#endif
+
+template <bool LBVH, bool DEFER_SKY, class Stack>
+__device__ __forceinline__ unsigned warp_step(Path &p, Walk &w, Stack &st, const RtRenderParams &P, const SharedScene &S)
 {
 	unsigned traced = 0;
-	if (p.mode == MODE_TRACE) {
-		f3 ro = p.ray_o;
-		f3 dn = unit3(p.ray_d);             /* scene.c:158 */
-		RayQ q = ray_quadratic(dn);
-		Hit h;
-		if (LBVH) h = nearest_lbvh(P.bvh, P.scene.geomA, P.scene.geomB, ro, dn, q);
-		else      h = nearest_linear(S.A, S.B, S.runs, P.scene.num_runs, P.scene.n, ro, dn, q, P.scene.div_safe);
-		traced = 1;
-		path_classify<DEFER_SKY>(p, h, dn, P.scene, P.sky, S.lut,
-		              [&](const Hit &hh, f3 d, f3 &point, f3 &normal) {
-			              if (LBVH) surface_of(hh, __ldg(&P.scene.geomA[hh.obj]), __ldg(&P.scene.geomB[hh.obj]), ro, d, point, normal);
-			              else      surface_of(hh, S.A[2 * hh.obj], S.B[2 * hh.obj], ro, d, point, normal);
-		              });
+	if (!LBVH) {
+		if (p.mode == MODE_TRACE) {
+			f3 ro = p.ray_o;
+			f3 dn = unit3(p.ray_d);             /* scene.c:158 */
+			RayQ q = ray_quadratic(dn);
+			Hit h = nearest_linear(S.A, S.B, S.runs, P.scene.num_runs, P.scene.n, ro, dn, q, P.scene.div_safe);
+			traced = 1;
+			path_classify<DEFER_SKY>(p, h, dn, P.scene, P.sky, S.lut,
+			              [&](const Hit &hh, f3 d, f3 &point, f3 &normal) {
+				              surface_of(hh, S.A[2 * hh.obj], S.B[2 * hh.obj], ro, d, point, normal);
+			              });
+		}
+	} else {
+		const unsigned full = 0xffffffffu;
+		if (p.mode == MODE_TRACE) {
+			p.ray_d = unit3(p.ray_d);           /* scene.c:158; kept for the steps the walk lasts */
+			walk_begin(w, P.bvh);
+			p.mode = MODE_WALK;
+			traced = 1;
+		}
+		const bool walking = p.mode == MODE_WALK;
+		const f3 ro = p.ray_o, dn = p.ray_d;
+		if (walking) walk_nodes(P.bvh, ro, walk_inverse(dn), w, st, RT_WALK_ITERS);
+		__syncwarp();
+		int prim = 0;
+		float nb = 0.0f, discr = 0.0f;
+		bool roots = false;
+		if (walking && w.leaf) roots = walk_leaf_screen(P.bvh, ro, dn, w, prim, nb, discr);
+		__syncwarp();
+		if (roots) walk_leaf_root(dn, prim, nb, discr, w);
+		__syncwarp();
+		if (walking && walk_over(w)) p.mode = MODE_HIT;
+		const unsigned hits = __ballot_sync(full, p.mode == MODE_HIT);
+		if (hits == 0) return traced;
+		if (__popc(hits) < RT_WALK_HOLD && __any_sync(full, p.mode == MODE_WALK)) return traced;
+		if (p.mode == MODE_HIT)
+			path_classify<DEFER_SKY>(p, w.best, dn, P.scene, P.sky, S.lut,
+			              [&](const Hit &hh, f3 d, f3 &point, f3 &normal) {
+				              surface_of(hh, __ldg(&P.scene.geomA[hh.obj]), __ldg(&P.scene.geomB[hh.obj]), ro, d, point, normal);
+			              });
 	}
 	warp_sweep(p, S.sweep, P.sweep_tau2);
 	if (p.mode == MODE_LAUNCH) path_launch(p, P.scene);
@@ -236,6 +283,9 @@ render_pixel_kernel(const __grid_constant__ RtRenderParams P)
 	int cx, cy;
 	Path p;
 	p.mode = MODE_IDLE;
+	Walk w;
+	SharedStack st;
+	stack_init(st, S);
 	Cell c;
 	bool owns = idx < (unsigned) (P.tiles_x * P.tiles_y) * 32u && cell_of(P, idx, cx, cy);
 	if (owns) {
@@ -243,7 +293,7 @@ render_pixel_kernel(const __grid_constant__ RtRenderParams P)
 		path_begin(p, P.cam, c.u, c.v, P.pass_mix);
 	}
 	while (__any_sync(full, p.mode != MODE_IDLE))
-		rays += warp_step<LBVH>(p, P, S);
+		rays += warp_step<LBVH, false>(p, w, st, P, S);
 	if (owns) store_cell(P, c, path_final(p));
 	count_rays(P, rays);
 }
@@ -254,12 +304,17 @@ render_pixel_kernel(const __grid_constant__ RtRenderParams P)
 #define RT_PERSISTENT_MIN_BLOCKS 6   /* 80 registers, 24 warps/SM: best of 5/6/8 on 4K scene_0 (2.39 / 2.37 / 2.51 ms) */
 #endif
 
-/* the LBVH walk is bound by node-fetch latency (ncu: long-scoreboard stalls), so
- * it trades registers for resident warps: 8 CTAs/SM (64 registers) */
-template <bool LBVH>
-__global__ void __launch_bounds__(RT_BLOCK_THREADS, LBVH ? 8 : RT_PERSISTENT_MIN_BLOCKS)
+#ifndef RT_LBVH_MIN_BLOCKS
+#define RT_LBVH_MIN_BLOCKS 5         /* LBVH kernels: path + walk state live across warp steps */
+#endif
+
+/* TRAV: 0 = linear scan from shared memory, 1 = LBVH with the traversal stacks in
+ * shared memory, 2 = LBVH with local-memory stacks (trees deeper than RT_SMEM_STACK) */
+template <int TRAV>
+__global__ void __launch_bounds__(RT_BLOCK_THREADS, TRAV ? RT_LBVH_MIN_BLOCKS : RT_PERSISTENT_MIN_BLOCKS)
 render_persistent_kernel(const __grid_constant__ RtRenderParams P)
 {
+	constexpr bool LBVH = TRAV != 0;
 	extern __shared__ __align__(16) unsigned char smem[];
 	SharedScene S = stage_scene(P, smem, !LBVH);
 
@@ -269,6 +324,9 @@ render_persistent_kernel(const __grid_constant__ RtRenderParams P)
 
 	Path p;
 	p.mode = MODE_IDLE;
+	Walk w;
+	typename std::conditional<TRAV == 2, LocalStack, SharedStack>::type st;
+	stack_init(st, S);
 	Cell c;
 	bool owns = false;          /* lane holds a pixel whose path is running or just ended */
 	unsigned rays = 0;
@@ -319,7 +377,7 @@ render_persistent_kernel(const __grid_constant__ RtRenderParams P)
 			if (exhausted && batch_next == batch_end) break;
 			continue;       /* only clipped cells were handed out; fetch more */
 		}
-		rays += warp_step<LBVH>(p, P, S);
+		rays += warp_step<LBVH, false>(p, w, st, P, S);
 	}
 	count_rays(P, rays);
 }
@@ -403,7 +461,7 @@ __device__ __forceinline__ void rq_drain(const RtRenderParams &P, const SharedSc
 #endif
 
 template <bool LBVH>
-__global__ void __launch_bounds__(RT_BLOCK_THREADS, LBVH ? 8 : RT_QUEUED_MIN_BLOCKS)
+__global__ void __launch_bounds__(RT_BLOCK_THREADS, LBVH ? RT_LBVH_MIN_BLOCKS : RT_QUEUED_MIN_BLOCKS)
 render_queued_kernel(const __grid_constant__ RtRenderParams P)
 {
 	extern __shared__ __align__(16) unsigned char smem[];
@@ -419,6 +477,9 @@ render_queued_kernel(const __grid_constant__ RtRenderParams P)
 	Path p;
 	p.mode = MODE_IDLE;
 	p.obj = 0;
+	Walk w;
+	SharedStack st;
+	stack_init(st, S);
 	int cx0 = 0, cy0 = 0, ctw = 0;  /* output tile of the lane's pixel */
 	bool owns = false;              /* lane holds a pixel whose path is running or just ended */
 	unsigned rays = 0;
@@ -541,7 +602,7 @@ render_queued_kernel(const __grid_constant__ RtRenderParams P)
 			__syncwarp();
 		}
 		if (over) break;
-		rays += warp_step<LBVH, true>(p, P, S);
+		rays += warp_step<LBVH, true>(p, w, st, P, S);
 	}
 	count_rays(P, rays);
 }
@@ -664,7 +725,8 @@ render_wavefront_kernel(const __grid_constant__ RtRenderParams P)
 	extern __shared__ __align__(16) unsigned char smem[];
 	SharedScene S = stage_scene(P, smem, !LBVH);
 	size_t scene_bytes = 256 * sizeof(float) + RT_BLOCK_THREADS +
-	                     (LBVH ? 0 : 2 * sizeof(float4) * (size_t) P.scene.n + sizeof(int2) * (size_t) P.scene.num_runs);
+	                     (LBVH ? sizeof(int) * RT_SMEM_STACK * RT_BLOCK_THREADS
+	                           : 2 * sizeof(float4) * (size_t) P.scene.n + sizeof(int2) * (size_t) P.scene.num_runs);
 	scene_bytes = (scene_bytes + 15) & ~(size_t) 15;
 	const unsigned full = 0xffffffffu;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -766,7 +828,7 @@ render_wavefront_kernel(const __grid_constant__ RtRenderParams P)
 				f3 dn = unit3(pool.get3(WF_RD, s));  /* scene.c:158 */
 				RayQ q = ray_quadratic(dn);
 				Hit h;
-				if (LBVH) h = nearest_lbvh(P.bvh, P.scene.geomA, P.scene.geomB, ro, dn, q);
+				if (LBVH) { LocalStack ls; h = nearest_lbvh(P.bvh, ro, dn, ls); }
 				else      h = nearest_linear(S.A, S.B, S.runs, P.scene.num_runs, P.scene.n, ro, dn, q, P.scene.div_safe);
 				rays++;
 				if (st & WF_SHADOW) {
@@ -846,7 +908,7 @@ __global__ void probe_trace_kernel(RtRenderParams P, const float *rays6, int n, 
 	f3 d = unit3(mk(rays6[6 * i + 3], rays6[6 * i + 4], rays6[6 * i + 5]));
 	RayQ q = ray_quadratic(d);
 	Hit h;
-	if (LBVH) h = nearest_lbvh(P.bvh, P.scene.geomA, P.scene.geomB, o, d, q);
+	if (LBVH) { LocalStack ls; h = nearest_lbvh(P.bvh, o, d, ls); }
 	else      h = nearest_linear(S.A, S.B, S.runs, P.scene.num_runs, P.scene.n, o, d, q, P.scene.div_safe);
 	float *r = out7 + 7 * (size_t) i;
 	obj[i] = h.obj;
@@ -935,7 +997,8 @@ __global__ void probe_div_kernel(uint64_t seed, unsigned per_thread, int lo_exp_
 static size_t smem_bytes(const RtRenderParams &P, bool lbvh)
 {
 	return 256 * sizeof(float) + RT_BLOCK_THREADS +
-	       (lbvh ? 0 : 2 * sizeof(float4) * (size_t) P.scene.n + sizeof(int2) * (size_t) P.scene.num_runs);
+	       (lbvh ? sizeof(int) * RT_SMEM_STACK * RT_BLOCK_THREADS      /* traversal stacks */
+	             : 2 * sizeof(float4) * (size_t) P.scene.n + sizeof(int2) * (size_t) P.scene.num_runs);
 }
 
 template <class K>
@@ -964,6 +1027,13 @@ extern "C" cudaError_t RT_FN(launch_render)(const RtRenderParams *P, int lbvh, i
 	unsigned total = (unsigned) (P->tiles_x * P->tiles_y) * 32u;
 	if (total == 0) return cudaSuccess;
 	cudaError_t e;
+	if (lbvh && P->bvh.depth > RT_SMEM_STACK) {
+		/* a tree deeper than the shared-memory stacks (degenerate scenes): the
+		 * local-memory-stack build of the persistent kernel, whatever was asked for */
+		if ((e = allow_smem(render_persistent_kernel<2>, sm)) != cudaSuccess) return e;
+		render_persistent_kernel<2><<<grid_blocks, RT_BLOCK_THREADS, sm, stream>>>(*P);
+		return cudaGetLastError();
+	}
 	if (persistent == 3) {      /* persistent kernel with finish / refill queues */
 		size_t qsm = queued_smem_bytes(*P, lbvh != 0);
 		if (lbvh) {
@@ -988,11 +1058,11 @@ extern "C" cudaError_t RT_FN(launch_render)(const RtRenderParams *P, int lbvh, i
 	}
 	if (persistent) {
 		if (lbvh) {
-			if ((e = allow_smem(render_persistent_kernel<true>, sm)) != cudaSuccess) return e;
-			render_persistent_kernel<true><<<grid_blocks, RT_BLOCK_THREADS, sm, stream>>>(*P);
+			if ((e = allow_smem(render_persistent_kernel<1>, sm)) != cudaSuccess) return e;
+			render_persistent_kernel<1><<<grid_blocks, RT_BLOCK_THREADS, sm, stream>>>(*P);
 		} else {
-			if ((e = allow_smem(render_persistent_kernel<false>, sm)) != cudaSuccess) return e;
-			render_persistent_kernel<false><<<grid_blocks, RT_BLOCK_THREADS, sm, stream>>>(*P);
+			if ((e = allow_smem(render_persistent_kernel<0>, sm)) != cudaSuccess) return e;
+			render_persistent_kernel<0><<<grid_blocks, RT_BLOCK_THREADS, sm, stream>>>(*P);
 		}
 	} else {
 		unsigned blocks = (total + RT_BLOCK_THREADS - 1) / RT_BLOCK_THREADS;
@@ -1038,11 +1108,11 @@ extern "C" cudaError_t RT_FN(persistent_blocks_per_sm)(const RtRenderParams *P, 
 		return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, render_queued_kernel<false>, RT_BLOCK_THREADS, sm);
 	}
 	if (lbvh) {
-		if ((e = allow_smem(render_persistent_kernel<true>, sm)) != cudaSuccess) return e;
-		return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, render_persistent_kernel<true>, RT_BLOCK_THREADS, sm);
+		if ((e = allow_smem(render_persistent_kernel<1>, sm)) != cudaSuccess) return e;
+		return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, render_persistent_kernel<1>, RT_BLOCK_THREADS, sm);
 	}
-	if ((e = allow_smem(render_persistent_kernel<false>, sm)) != cudaSuccess) return e;
-	return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, render_persistent_kernel<false>, RT_BLOCK_THREADS, sm);
+	if ((e = allow_smem(render_persistent_kernel<0>, sm)) != cudaSuccess) return e;
+	return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, render_persistent_kernel<0>, RT_BLOCK_THREADS, sm);
 }
 
 extern "C" cudaError_t RT_FN(launch_probe_trace)(const RtRenderParams *P, int lbvh, const float *rays6, int n,
