@@ -3,6 +3,7 @@
 #   make            build the product library in-tree (ray_tracing_b200/)
 #   make oracle     build the test-only checkers (oracle/)
 #   make harness    build the headless C harness (tools/rt_headless)
+# `make` also builds tools/librt_skybox_stb.so when the reference's 3p/ is present.
 NVCC      ?= /usr/local/cuda/bin/nvcc
 CC        ?= gcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
@@ -10,6 +11,7 @@ SRC       := ray_tracing_b200/csrc
 OBJ       := build/obj
 LIB       := ray_tracing_b200/libraytrace_b200.so
 HARNESS   := tools/rt_headless
+SKYLIB    := tools/librt_skybox_stb.so
 STB_DIR   ?= /root/reference/3p
 NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Iinclude -I$(SRC) -Xcompiler -fPIC -Xcompiler -ffp-contract=off \
              --expt-relaxed-constexpr -Xptxas -v $(NVFLAGS_EXTRA)
@@ -21,7 +23,7 @@ CUDA_OBJS := $(OBJ)/rt_api.o $(OBJ)/rt_lbvh.o $(OBJ)/rt_render_exact.o $(OBJ)/rt
 DEVICE_HDRS := $(SRC)/rt_device.cuh $(SRC)/rt_params.h $(SRC)/rt_host.h $(SRC)/rt_lbvh.h $(SRC)/rt_lbvh_rule.h include/rt_cuda.h
 
 .PHONY: all oracle harness clean
-all: $(LIB) $(HARNESS)
+all: $(LIB) $(HARNESS) $(if $(wildcard $(STB_DIR)/stb/stb_image.h),$(SKYLIB),)
 
 $(OBJ)/%.o: $(SRC)/%.c include/rt_cuda.h $(SRC)/rt_host.h
 	@mkdir -p $(OBJ)
@@ -55,6 +57,11 @@ harness: $(HARNESS)
 $(HARNESS): tools/rt_headless.c include/rt_cuda.h $(LIB)
 	$(CC) -std=c11 -O2 -Iinclude $(if $(wildcard $(STB_DIR)/stb/stb_image.h),-DRT_HAVE_STB -I$(STB_DIR),) \
 	    -o $@ tools/rt_headless.c -Lray_tracing_b200 -lraytrace_b200 -Wl,-rpath,'$$ORIGIN/../ray_tracing_b200' -lm
+
+# the reference's JPEG decoder (stb_image, compiled from the reference's 3p/ in place)
+# for Python hosts: bench.py and the tests feed the texels the reference would
+$(SKYLIB): tools/rt_skybox_stb.c
+	$(CC) -std=c11 -O2 -fPIC -shared -w -I$(STB_DIR) -o $@ $< -lm
 
 clean:
 	rm -rf build $(LIB)

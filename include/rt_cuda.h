@@ -201,6 +201,13 @@ typedef struct {
 	                           /*    it is valid after rt_cuda_synchronize()                                      */
 	int      remote_fb;        /* 1: `fb` is peer memory (another GPU's frame): render locally, then copy    */
 	                           /*    the owned blocks there with one strided device-to-device copy           */
+	uint32_t frame_seq;        /* remote_fb only, `fb` from rt_cuda_shared_frame_*: 0 = the copy follows the  */
+	                           /*    render on the same stream.  s >= 1 (consecutive per frame) = pipelined   */
+	                           /*    composite: the call returns after queueing; the copy of frame s runs on  */
+	                           /*    the copy stream while frame s+1 renders, then marks this rank's blocks   */
+	                           /*    of frame s as arrived (rt_cuda_shared_frame_wait)                        */
+	int      frame_ack;        /* frame_seq only: do not overwrite the shared frame with frame s before the  */
+	                           /*    owner released frame s-1 (rt_cuda_shared_frame_release)                  */
 } RtRenderOpts;
 
 typedef struct {
@@ -244,6 +251,20 @@ int rt_cuda_render_sweep(const RtCamera *cam, void *fb, int w, int h, int init_s
 int rt_cuda_shared_frame_create(size_t bytes, void **dev_ptr, void *handle64);
 int rt_cuda_shared_frame_open(const void *handle64, void **dev_ptr);
 int rt_cuda_shared_frame_close(void *dev_ptr, int owner);
+/* Pipelined composite (opts->frame_seq): the frame carries a small header of
+ * flag words in the owner's memory.  Every rank -- the owner too, with
+ * remote_fb = 1 -- renders frame s into one of two local frames and ships its
+ * blocks on its copy stream while it already renders frame s+1; after the copy
+ * it writes s into its `arrived` word.
+ *   wait     owner: work queued on `stream` after this call starts once the
+ *            blocks of frame `seq` of all `num_ranks` ranks have landed;
+ *   release  owner: frame `seq` has been consumed; ranks rendering with
+ *            opts->frame_ack may overwrite it with frame seq+1.
+ * Both are stream operations (tiny polling kernels with a 2 s timeout that
+ * raises the header's error word; rt_cuda_shared_frame_error reads it). */
+int rt_cuda_shared_frame_wait(void *dev_ptr, int num_ranks, uint32_t seq, void *stream);
+int rt_cuda_shared_frame_release(void *dev_ptr, uint32_t seq, void *stream);
+int rt_cuda_shared_frame_error(void *dev_ptr, uint32_t *error_out);
 int rt_cuda_copy_to_host(void *host_dst, const void *dev_src, size_t bytes, void *stream);
 
 /* The reference's frame scheduler (main.c:324-482) in three calls:

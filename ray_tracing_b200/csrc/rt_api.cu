@@ -181,7 +181,13 @@ static int init_devices(const int *devices, int count)
 		CU(cudaSetDevice(d.device));
 		CU(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, d.device));
 		CU(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
-		CU(cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking));
+		{
+			/* the copy stream also runs the tiny flag kernels of the pipelined composite: highest
+			 * priority, so that they take the first free warp slot next to a resident render grid */
+			int lo_prio = 0, hi_prio = 0;
+			CU(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+			CU(cudaStreamCreateWithPriority(&d.copy_stream, cudaStreamNonBlocking, hi_prio));
+		}
 		for (int k = 0; k < 2; k++) {
 			CU(cudaEventCreateWithFlags(&d.stage_rendered[k], cudaEventDisableTiming));
 			CU(cudaEventCreateWithFlags(&d.stage_copied[k], cudaEventDisableTiming));
@@ -276,6 +282,11 @@ extern "C" int rt_cuda_upload_objects(const RtObject *objects, int n)
 		runs.push_back(make_int2(i, (j - i) | ((ty & 0x7f) << 24)));
 		i = j;
 	}
+	/* from here on the old scene is gone on at least one device: a failure below
+	 * must not leave the context claiming it still has one */
+	g.have_scene = false;
+	g.have_bvh = false;
+	g.scene_epoch++;
 	for (int i = 0; i < g.ngpu; i++) {
 		DeviceCtx &d = g.dev[i];
 		if ((rc = select_device(d)) != RT_OK) { rt_host_free_packed(&ps); return rc; }
@@ -313,7 +324,6 @@ extern "C" int rt_cuda_upload_objects(const RtObject *objects, int n)
 	g.div_safe = ps.div_safe;
 	g.num_runs = (int) runs.size();
 	g.have_scene = true;
-	g.scene_epoch++;
 	g.have_bvh = want_bvh;
 	rt_host_free_packed(&ps);
 	cudaSetDevice(g.dev[0].device);
@@ -326,7 +336,10 @@ extern "C" int rt_cuda_upload_scene(const RtScene *scene)
 	if (scene->num_objects < 0 || scene->num_objects > RT_MAX_OBJECTS)
 		return fail(RT_ERR_ARG, "scene->num_objects = %d out of range", scene->num_objects);
 	int rc = rt_cuda_upload_objects(scene->objects, scene->num_objects);
-	if (rc != RT_OK) return rc;
+	if (rc != RT_OK) {
+		if (g.scene_cache) g.scene_cache->num_objects = -1;    /* never equal to a caller's scene */
+		return rc;
+	}
 	if (!g.scene_cache) g.scene_cache = (RtScene *) malloc(sizeof(RtScene));
 	if (g.scene_cache) {
 		memcpy(g.scene_cache->objects, scene->objects, sizeof(RtObject) * (size_t) scene->num_objects);
@@ -487,6 +500,68 @@ static int interleave_shift(int scale)
 	return sh;       /* low-res rows per block = 1 << shift */
 }
 
+/* ---- pipelined composite: flag words in front of a shared frame ---------- */
+
+/* rt_cuda_shared_frame_create() allocates this header in the owner's memory,
+ * RT_SHARED_HEADER_BYTES before the address it returns; the other ranks see it
+ * through their cudaIpc mapping of the same allocation. */
+#define RT_SHARED_HEADER_BYTES 4096
+struct SharedHeader {
+	unsigned int arrived[RT_MAX_GPUS];   /* arrived[r] = last frame whose blocks rank r has copied in */
+	unsigned int consumed;               /* last frame the owner released */
+	unsigned int error;                  /* a polling kernel gave up (bit 0: wait, bit 1: ack) */
+};
+
+static SharedHeader *header_of(void *frame) { return (SharedHeader *) ((char *) frame - RT_SHARED_HEADER_BYTES); }
+
+__device__ __forceinline__ unsigned long long global_ns(void)
+{
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+
+/* seq numbers wrap: a is at or past b */
+__device__ __forceinline__ bool seq_reached(unsigned a, unsigned b) { return (int) (a - b) >= 0; }
+
+#define RT_FLAG_TIMEOUT_NS 2000000000ull
+
+/* after this rank's blocks of frame `seq` were copied (same stream) */
+__global__ void flag_arrive_kernel(SharedHeader *h, int rank, unsigned seq)
+{
+	__threadfence_system();
+	*(volatile unsigned int *) &h->arrived[rank] = seq;
+}
+
+/* owner: returns once every rank's blocks of frame `seq` have landed */
+__global__ void flag_wait_kernel(SharedHeader *h, int num_ranks, unsigned seq)
+{
+	int r = threadIdx.x;
+	if (r >= num_ranks) return;
+	unsigned long long t0 = global_ns();
+	while (!seq_reached(*(volatile unsigned int *) &h->arrived[r], seq)) {
+		__nanosleep(200);
+		if (global_ns() - t0 > RT_FLAG_TIMEOUT_NS) { atomicOr(&h->error, 1u); break; }
+	}
+	__threadfence_system();
+}
+
+__global__ void flag_release_kernel(SharedHeader *h, unsigned seq)
+{
+	__threadfence_system();
+	*(volatile unsigned int *) &h->consumed = seq;
+}
+
+/* any rank, before overwriting the shared frame with frame `seq`: the owner is done with seq - 1 */
+__global__ void flag_ack_kernel(SharedHeader *h, unsigned seq)
+{
+	unsigned long long t0 = global_ns();
+	while (!seq_reached(*(volatile unsigned int *) &h->consumed, seq - 1u)) {
+		__nanosleep(500);
+		if (global_ns() - t0 > RT_FLAG_TIMEOUT_NS) { atomicOr(&h->error, 2u); break; }
+	}
+}
+
 /* Copy the row blocks this GPU owns (interleave il_i of il_n) from its local
  * frame to the same rows of `dst` (GPU 0's frame, peer memory) with the copy
  * engine.  The render kernel stores 4-byte words pixel by pixel as paths end;
@@ -514,6 +589,45 @@ static int copy_owned_blocks(void *dst, const void *src, const PassPlan &pl, int
 	if (own_partial_last) {
 		size_t off = (size_t) (pl.row0 - fb_row_offset) * row_bytes + (size_t) last * chunk;
 		CU(cudaMemcpyAsync((char *) dst + off, (const char *) src + off, (size_t) last_rows * row_bytes, kind, stream));
+	}
+	return RT_OK;
+}
+
+/* Pixels the reference's pass never writes (main.c:285-290: rows >= lh*scale;
+ * main.c:363: columns >= T*column_w) hold 0.  Every GPU clears them in ITS
+ * render target and only inside the row blocks it owns (copy_owned_blocks ships
+ * whole rows of exactly those blocks), so no two GPUs ever write the same byte. */
+static int clear_uncovered_owned(void *fb, const PassPlan &pl, int fb_row_offset, int il_n, int il_i, size_t bpp,
+                                 int covered_rows_end, bool columns_uncovered, cudaStream_t stream, int *launches)
+{
+	int rows_per_block = (1 << interleave_shift(pl.scale)) * pl.scale;
+	int band = pl.row1 - pl.row0;
+	size_t row_bytes = (size_t) pl.w * bpp;
+	size_t chunk = (size_t) rows_per_block * row_bytes;
+	int nblocks = (band + rows_per_block - 1) / rows_per_block;
+	int last = nblocks - 1;
+	int last_rows = band - last * rows_per_block;
+	char *base = (char *) fb + (size_t) (pl.row0 - fb_row_offset) * row_bytes;
+	if (columns_uncovered) {
+		/* rare (W % T != 0): zero every owned row, the launch then fills the covered pixels */
+		int mine = il_i < nblocks ? (nblocks - 1 - il_i) / il_n + 1 : 0;
+		bool own_last = mine > 0 && last % il_n == il_i;
+		int full = own_last && last_rows != rows_per_block ? mine - 1 : mine;
+		if (full > 0) {
+			CU(cudaMemset2DAsync(base + (size_t) il_i * chunk, (size_t) il_n * chunk, 0, chunk, (size_t) full, stream));
+			(*launches)++;
+		}
+		if (own_last && last_rows != rows_per_block) {
+			CU(cudaMemsetAsync(base + (size_t) last * chunk, 0, (size_t) last_rows * row_bytes, stream));
+			(*launches)++;
+		}
+		return RT_OK;
+	}
+	if (covered_rows_end < pl.row1 && last % il_n == il_i) {
+		/* rows [lh*scale, H) lie in the last block */
+		int s0 = std::max(covered_rows_end, pl.row0);
+		CU(cudaMemsetAsync((char *) fb + (size_t) (s0 - fb_row_offset) * row_bytes, 0, (size_t) (pl.row1 - s0) * row_bytes, stream));
+		(*launches)++;
 	}
 	return RT_OK;
 }
@@ -668,18 +782,13 @@ static int launch_band(DeviceCtx &d, const RtCamera *cam, const PassPlan &pl, co
 	P.accum_weight = accum_weight;
 	P.inv_count = inv_count;
 
-	/* Pixels the reference's pass never writes (main.c:285-290: rows >=
-	 * lh*scale; main.c:363: columns >= T*column_w) hold 0: a fresh frame is
-	 * zeroed there, and an accumulated frame never receives data there, so its
-	 * accum/count is 0 too.  One GPU (interleave index 0) clears them. */
+	/* pixels the reference's pass never writes hold 0 (clear_uncovered_owned) */
 	int covered_rows_end = std::min(P.lh * pl.scale, r1);
-	bool uncovered = covered_rows_end < r1 || P.column_w * pl.ncols < pl.w;
-	size_t bpp = bytes_per_pixel(o->fb_format);
-	if (uncovered && P.il_i == 0) {
-		int s0 = P.column_w * pl.ncols < pl.w ? r0 : std::max(covered_rows_end, r0);
-		CU(cudaMemsetAsync((char *) fb + (size_t) (s0 - fb_row_offset) * pl.w * bpp, 0,
-		                   (size_t) (r1 - s0) * pl.w * bpp, stream));
-		(*launches)++;
+	bool columns_uncovered = P.column_w * pl.ncols < pl.w;
+	if (covered_rows_end < r1 || columns_uncovered) {
+		int rc = clear_uncovered_owned(fb, pl, fb_row_offset, P.il_n, P.il_i, bytes_per_pixel(o->fb_format),
+		                               covered_rows_end, columns_uncovered, stream, launches);
+		if (rc != RT_OK) return rc;
 	}
 
 	if (P.tiles_x > 0 && P.tiles_y > 0) {
@@ -755,8 +864,10 @@ static int validate_common(const RtCamera *cam, void *fb, int w, int h, const Rt
 	return RT_OK;
 }
 
+/* ship = false: a pass of a sweep whose frame nobody will look at (only the accumulation
+ * matters): a rank with a remote frame renders it locally and sends nothing */
 static int render_pass(const RtCamera *cam, void *fb, int w, int h, const RtRenderOpts *o,
-                       bool accumulate, RtRenderStats *stats, bool sync_and_copy)
+                       bool accumulate, RtRenderStats *stats, bool sync_and_copy, bool ship = true)
 {
 	PassPlan pl;
 	pl.w = w; pl.h = h; pl.scale = o->scale; pl.ncols = o->num_columns;
@@ -774,6 +885,9 @@ static int render_pass(const RtCamera *cam, void *fb, int w, int h, const RtRend
 	pl.queued = (o->kernel == RT_KERNEL_QUEUED || (o->kernel == RT_KERNEL_AUTO && !pl.lbvh)) && o->scale <= 64;   /* tile width is packed into 7 bits */
 	pl.persistent = o->kernel == RT_KERNEL_PERSISTENT || o->kernel == RT_KERNEL_AUTO || pl.queued;
 	pl.wavefront = o->kernel == RT_KERNEL_WAVEFRONT;
+	/* the wavefront kernel packs the tile width into 5 bits and a pixel's x, y into 16 bits each */
+	if (pl.wavefront && (o->scale > 31 || w > 65535 || h > 65535))
+		return fail(RT_ERR_ARG, "RT_KERNEL_WAVEFRONT supports scale <= 31 and frames up to 65535x65535");
 
 	size_t bpp = bytes_per_pixel(o->fb_format);
 	int band_rows = pl.row1 - pl.row0;
@@ -788,20 +902,24 @@ static int render_pass(const RtCamera *cam, void *fb, int w, int h, const RtRend
 	 * call already renders into the other one; the call returns without waiting.
 	 * `fb` is valid after rt_cuda_synchronize() (or once two later calls returned). */
 	bool pipelined = !dev_fb && o->pipeline && g.ngpu == 1 && !stats;
+	/* Pipelined composite into a shared frame (opts->frame_seq): same two staging
+	 * frames, but the copy stream ships the owned blocks to peer memory and then
+	 * raises this rank's `arrived` flag in the frame's header. */
+	bool piped_peer = ship && dev_fb && o->interleave_count > 1 && o->remote_fb && o->frame_seq != 0 && g.ngpu == 1 && !stats;
 	int slot = 0;
-	if (pipelined) {
+	if (pipelined || piped_peer) {
 		size_t need = fb_rows * (size_t) w * bpp;
 		if ((rc = select_device(d0)) != RT_OK) return rc;
 		slot = d0.stage_next;
 		d0.stage_next ^= 1;
-		CU(cudaEventSynchronize(d0.stage_copied[slot]));       /* the copy that last used this slot */
+		if (pipelined) CU(cudaEventSynchronize(d0.stage_copied[slot]));       /* the copy that last used this slot */
 		if (d0.stage_bytes[slot] < need) {
 			CU(cudaFree(d0.stage[slot]));
 			d0.stage[slot] = nullptr; d0.stage_bytes[slot] = 0;
 			CU(cudaMalloc(&d0.stage[slot], need));
 			d0.stage_bytes[slot] = need;
 		}
-		target = d0.stage[slot];
+		if (pipelined) target = d0.stage[slot];
 	} else
 	if (!dev_fb) {
 		size_t need = fb_rows * (size_t) w * bpp;
@@ -826,6 +944,7 @@ static int render_pass(const RtCamera *cam, void *fb, int w, int h, const RtRend
 		if (o->interleave_index < 0 || o->interleave_index >= o->interleave_count)
 			return fail(RT_ERR_ARG, "interleave_index out of range");
 		if (ngpu > 1) return fail(RT_ERR_ARG, "interleave_count is for one-GPU-per-process ranks; this context already spans %d GPUs", ngpu);
+		if (o->interleave_count > RT_MAX_GPUS) return fail(RT_ERR_ARG, "interleave_count > %d", RT_MAX_GPUS);
 		il_n = o->interleave_count;
 		il_base = o->interleave_index;
 	} else if (ngpu > 1)
@@ -867,7 +986,11 @@ static int render_pass(const RtCamera *cam, void *fb, int w, int h, const RtRend
 		 * memory and ships the blocks it owns afterwards (copy_owned_blocks) */
 		bool remote = (ngpu > 1 && i > 0) || (o->interleave_count > 1 && o->remote_fb);
 		void *render_to = target;
-		if (remote) {
+		if (piped_peer) {
+			/* the render may reuse this staging frame once its last copy has left */
+			CU(cudaStreamWaitEvent(st, d.stage_copied[slot], 0));
+			render_to = d.stage[slot];
+		} else if (remote) {
 			size_t need = fb_rows * (size_t) w * bpp;
 			if (d.fb_bytes < need) {
 				CU(cudaFree(d.fb));
@@ -881,10 +1004,25 @@ static int render_pass(const RtCamera *cam, void *fb, int w, int h, const RtRend
 		rc = launch_band(d, cam, pl, o, render_to, fb_row_offset, pl.row0, pl.row1, il_n, il_i, st,
 		                 accumulate, wgt, inv, &launches);
 		if (rc != RT_OK) return rc;
-		if (remote && (rc = copy_owned_blocks(target, render_to, pl, fb_row_offset, il_n, il_i, bpp, st)) != RT_OK) return rc;
+		if (remote && ship && !piped_peer && (rc = copy_owned_blocks(target, render_to, pl, fb_row_offset, il_n, il_i, bpp, st)) != RT_OK) return rc;
 		if (stats) CU(cudaEventRecord(d.ev[1], st));
 	}
 
+	if (piped_peer) {
+		cudaStream_t st = use_user_stream ? (cudaStream_t) o->stream : d0.stream;
+		SharedHeader *hdr = header_of(fb);
+		CU(cudaEventRecord(d0.stage_rendered[slot], st));
+		CU(cudaStreamWaitEvent(d0.copy_stream, d0.stage_rendered[slot], 0));
+		if (o->frame_ack) {
+			flag_ack_kernel<<<1, 1, 0, d0.copy_stream>>>(hdr, o->frame_seq);
+			CU(cudaGetLastError());
+		}
+		if ((rc = copy_owned_blocks(fb, d0.stage[slot], pl, fb_row_offset, il_n, il_base, bpp, d0.copy_stream)) != RT_OK) return rc;
+		flag_arrive_kernel<<<1, 1, 0, d0.copy_stream>>>(hdr, il_base, o->frame_seq);
+		CU(cudaGetLastError());
+		CU(cudaEventRecord(d0.stage_copied[slot], d0.copy_stream));
+		return RT_OK;
+	}
 	if (pipelined) {
 		cudaStream_t st = use_user_stream ? (cudaStream_t) o->stream : d0.stream;
 		CU(cudaEventRecord(d0.stage_rendered[slot], st));
@@ -959,7 +1097,10 @@ extern "C" int render_frame_cuda_ex(const RtCamera *cam, void *fb, int w, int h,
 	RtRenderOpts def;
 	if (!opts) { rt_render_opts_default(&def); opts = &def; }
 	if ((rc = validate_common(cam, fb, w, h, opts)) != RT_OK) return rc;
-	return render_pass(cam, fb, w, h, opts, opts->accumulate != 0, stats, true);
+	/* a caller that names a stream and asks for no statistics gets stream-ordered
+	 * behaviour for a device frame: the call returns after queueing the launch */
+	bool wait = !(opts->stream && !stats && g.ngpu == 1);
+	return render_pass(cam, fb, w, h, opts, opts->accumulate != 0, stats, wait);
 }
 
 extern "C" int render_frame_cuda(const RtScene *scene, const RtCamera *cam, void *fb, int w, int h, int scale)
@@ -986,6 +1127,11 @@ extern "C" int rt_cuda_render_sweep(const RtCamera *cam, void *fb, int w, int h,
 	if (init_scale < 1 || (init_scale & (init_scale - 1))) return fail(RT_ERR_ARG, "init_scale must be a power of two");
 	RtRenderOpts o;
 	if (opts) o = *opts; else rt_render_opts_default(&o);
+	/* rows are dealt to GPUs / ranks in blocks of RT_INTERLEAVE_ROWS output rows so that a GPU owns the
+	 * same pixels (and its accumulation buffer stays valid) at every scale of the sweep: that holds
+	 * for scales up to the block size, which is also the reference's largest --init-scale (main.c:598) */
+	if (init_scale > RT_INTERLEAVE_ROWS && (g.ngpu > 1 || o.interleave_count > 1))
+		return fail(RT_ERR_ARG, "init_scale %d > %d is not supported when the frame is split over GPUs", init_scale, RT_INTERLEAVE_ROWS);
 	o.scale = init_scale;
 	if ((rc = validate_common(cam, fb, w, h, &o)) != RT_OK) return rc;
 	if ((rc = rt_cuda_accum_reset()) != RT_OK) return rc;          /* invalidate_accumulation() */
@@ -1015,7 +1161,9 @@ extern "C" int rt_cuda_render_sweep(const RtCamera *cam, void *fb, int w, int h,
 			dst = d0.fb;
 			oo.fb_memory = RT_MEM_DEVICE;
 		}
-		rc = render_pass(cam, dst, w, h, &oo, true, stats ? &st : nullptr, last);
+		/* with a caller stream, a device frame and no statistics the whole sweep is stream-ordered */
+		bool wait = last && !(dev_fb && o.stream && !stats && g.ngpu == 1);
+		rc = render_pass(cam, dst, w, h, &oo, true, stats ? &st : nullptr, wait, last || !oo.remote_fb);
 		if (rc != RT_OK) return rc;
 		total.rays += st.rays; total.pixels += st.pixels;
 		total.render_ms += st.render_ms; total.copy_ms += st.copy_ms;
@@ -1221,16 +1369,18 @@ extern "C" int rt_cuda_shared_frame_create(size_t bytes, void **dev_ptr, void *h
 	if (!dev_ptr || !handle64 || bytes == 0) return fail(RT_ERR_ARG, "bad shared frame request");
 	if ((rc = select_device(g.dev[0])) != RT_OK) return rc;
 	void *p = nullptr;
-	CU(cudaMalloc(&p, bytes));
+	CU(cudaMalloc(&p, bytes + RT_SHARED_HEADER_BYTES));
+	cudaError_t e = cudaMemset(p, 0, RT_SHARED_HEADER_BYTES);
 	cudaIpcMemHandle_t h;
-	cudaError_t e = cudaIpcGetMemHandle(&h, p);
+	if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
 	if (e != cudaSuccess) {
 		cudaFree(p);
-		return fail(RT_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+		return fail(RT_ERR_CUDA, "shared frame (cudaIpcGetMemHandle): %s", cudaGetErrorString(e));
 	}
 	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+	static_assert(sizeof(SharedHeader) <= RT_SHARED_HEADER_BYTES, "header size");
 	memcpy(handle64, &h, 64);
-	*dev_ptr = p;
+	*dev_ptr = (char *) p + RT_SHARED_HEADER_BYTES;
 	return RT_OK;
 }
 
@@ -1244,15 +1394,49 @@ extern "C" int rt_cuda_shared_frame_open(const void *handle64, void **dev_ptr)
 	memcpy(&h, handle64, 64);
 	void *p = nullptr;
 	CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-	*dev_ptr = p;
+	*dev_ptr = (char *) p + RT_SHARED_HEADER_BYTES;
 	return RT_OK;
 }
 
 extern "C" int rt_cuda_shared_frame_close(void *dev_ptr, int owner)
 {
 	if (!dev_ptr) return RT_OK;
-	if (owner) CU(cudaFree(dev_ptr));
-	else CU(cudaIpcCloseMemHandle(dev_ptr));
+	void *base = (char *) dev_ptr - RT_SHARED_HEADER_BYTES;
+	if (owner) CU(cudaFree(base));
+	else CU(cudaIpcCloseMemHandle(base));
+	return RT_OK;
+}
+
+extern "C" int rt_cuda_shared_frame_wait(void *dev_ptr, int num_ranks, uint32_t seq, void *stream)
+{
+	int rc = require_ready();
+	if (rc != RT_OK) return rc;
+	if (!dev_ptr || num_ranks < 1 || num_ranks > RT_MAX_GPUS) return fail(RT_ERR_ARG, "bad shared frame wait");
+	if ((rc = select_device(g.dev[0])) != RT_OK) return rc;
+	cudaStream_t st = stream ? (cudaStream_t) stream : g.dev[0].stream;
+	flag_wait_kernel<<<1, 32, 0, st>>>(header_of(dev_ptr), num_ranks, seq);
+	CU(cudaGetLastError());
+	return RT_OK;
+}
+
+extern "C" int rt_cuda_shared_frame_release(void *dev_ptr, uint32_t seq, void *stream)
+{
+	int rc = require_ready();
+	if (rc != RT_OK) return rc;
+	if (!dev_ptr) return fail(RT_ERR_ARG, "bad shared frame");
+	if ((rc = select_device(g.dev[0])) != RT_OK) return rc;
+	cudaStream_t st = stream ? (cudaStream_t) stream : g.dev[0].stream;
+	flag_release_kernel<<<1, 1, 0, st>>>(header_of(dev_ptr), seq);
+	CU(cudaGetLastError());
+	return RT_OK;
+}
+
+extern "C" int rt_cuda_shared_frame_error(void *dev_ptr, uint32_t *error_out)
+{
+	int rc = require_ready();
+	if (rc != RT_OK) return rc;
+	if (!dev_ptr || !error_out) return fail(RT_ERR_ARG, "bad shared frame");
+	CU(cudaMemcpy(error_out, &header_of(dev_ptr)->error, sizeof(uint32_t), cudaMemcpyDeviceToHost));
 	return RT_OK;
 }
 
@@ -1304,6 +1488,7 @@ static struct {
 	int      scale = 8;
 	uint64_t pass = 0;
 	uint32_t generation = 0;            /* accum_generation, main.c:59 */
+	int      w = 0, h = 0;              /* frame size of the last update_frame() */
 } g_loop;
 
 extern "C" int rt_cuda_set_progressive(int init_scale, int num_columns)
@@ -1337,6 +1522,10 @@ extern "C" int rt_cuda_update_frame(const RtCamera *cam, void *fb, int w, int h,
 	if (rc != RT_OK) return rc;
 	RtRenderOpts o;
 	if (opts) o = *opts; else rt_render_opts_default(&o);
+	/* a resized frame restarts the progressive sweep: realloc_frame_buffer() bumps
+	 * accum_generation and the workers go back to init_scale (main.c:416-444, 405-408) */
+	if ((g_loop.w || g_loop.h) && (g_loop.w != w || g_loop.h != h) && (rc = rt_cuda_invalidate_accumulation()) != RT_OK) return rc;
+	g_loop.w = w; g_loop.h = h;
 	o.num_columns = g_loop.num_columns;
 	o.scale = g_loop.scale;
 	if ((rc = validate_common(cam, fb, w, h, &o)) != RT_OK) return rc;

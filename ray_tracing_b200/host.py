@@ -82,6 +82,8 @@ class RtRenderOpts(C.Structure):
         ("interleave_index", C.c_int),
         ("pipeline", C.c_int),
         ("remote_fb", C.c_int),
+        ("frame_seq", C.c_uint32),
+        ("frame_ack", C.c_int),
     ]
 
 
@@ -214,6 +216,9 @@ def load_library() -> C.CDLL:
     L.rt_cuda_shared_frame_create.argtypes = [C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]
     L.rt_cuda_shared_frame_open.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     L.rt_cuda_shared_frame_close.argtypes = [C.c_void_p, C.c_int]
+    L.rt_cuda_shared_frame_wait.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p]
+    L.rt_cuda_shared_frame_release.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+    L.rt_cuda_shared_frame_error.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
     L.rt_cuda_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.rt_cuda_debug_set_sweep_threshold.argtypes = [C.c_float]
     L.rt_cuda_debug_set_tile_schedule.argtypes = [C.c_int]
@@ -352,6 +357,32 @@ def camera_snapshot() -> Camera:
     return _cam_from_struct(load_library().rt_camera_snapshot())
 
 
+SKYBOX_LIB_PATH = os.path.join(os.path.dirname(_HERE), "tools", "librt_skybox_stb.so")
+
+
+def load_skybox_dir(directory: str) -> np.ndarray:
+    """The caller's half of load_cubemap() (gpu_and_windowing.c:19-40): the six
+    face JPEGs of `directory` (main.c:500-507) decoded by the reference's own
+    decoder, stb_image, through tools/librt_skybox_stb.so.  Returns (6, h, w,
+    chan) uint8 in CubeFace order.  Raises when the helper library or a face is
+    missing -- callers that can live with other texels fall back explicitly."""
+    if not os.path.exists(SKYBOX_LIB_PATH):
+        raise FileNotFoundError(f"{SKYBOX_LIB_PATH} not built (make; needs the reference's 3p/stb at build time)")
+    L = C.CDLL(SKYBOX_LIB_PATH)
+    L.rt_skybox_load_dir.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.rt_skybox_free.argtypes = [C.c_void_p]
+    L.rt_skybox_free.restype = None
+    ptr, w, h, ch = C.c_void_p(), C.c_int(), C.c_int(), C.c_int()
+    if L.rt_skybox_load_dir(os.fsencode(directory), C.byref(ptr), C.byref(w), C.byref(h), C.byref(ch)) != 0:
+        raise FileNotFoundError(f"skybox faces not decodable in {directory}")
+    try:
+        n = 6 * w.value * h.value * ch.value
+        faces = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n,)).copy()
+    finally:
+        L.rt_skybox_free(ptr)
+    return faces.reshape(6, h.value, w.value, ch.value)
+
+
 def quantize_frame(frame: np.ndarray) -> np.ndarray:
     """screenshot()'s 8-bit rule (main.c:666-670)."""
     frame = np.ascontiguousarray(frame, dtype=np.float32)
@@ -464,7 +495,10 @@ class Renderer:
         _check(self.lib.render_frame_cuda_ex(C.byref(cam), C.c_void_p(ptr), w, h, C.byref(o), C.byref(st) if stats else None))
         return _stats_dict(st) if stats else None
 
-    def render_sweep(self, camera: Camera, w: int, h: int, init_scale: int, first_pass: int = 0, *, out=None, ptr=None, stats=True, **opts):
+    def render_sweep(self, camera: Camera, w: int, h: int, init_scale: int, first_pass: int = 0, *, out=None, ptr=None, stats=True, host: bool = False, **opts):
+        """The 16 -> 1 progressive sweep (main.c:354, 402-403) into a numpy frame
+        (`out`, or a fresh one) or into caller memory at `ptr` (device pointer
+        unless host=True)."""
         o = self._opts(**opts)
         if ptr is None:
             if out is None:
@@ -472,7 +506,7 @@ class Renderer:
             o.fb_memory = RT_MEM_HOST
             dst = out.ctypes.data
         else:
-            o.fb_memory = RT_MEM_DEVICE
+            o.fb_memory = RT_MEM_HOST if host else RT_MEM_DEVICE
             dst = ptr
         st = RtRenderStats()
         cam = camera.as_struct()
@@ -494,6 +528,17 @@ class Renderer:
 
     def shared_frame_close(self, ptr: int, owner: bool) -> None:
         _check(self.lib.rt_cuda_shared_frame_close(C.c_void_p(ptr), 1 if owner else 0))
+
+    def shared_frame_wait(self, ptr: int, num_ranks: int, seq: int, stream=None) -> None:
+        _check(self.lib.rt_cuda_shared_frame_wait(C.c_void_p(ptr), int(num_ranks), int(seq), C.c_void_p(stream) if stream else None))
+
+    def shared_frame_release(self, ptr: int, seq: int, stream=None) -> None:
+        _check(self.lib.rt_cuda_shared_frame_release(C.c_void_p(ptr), int(seq), C.c_void_p(stream) if stream else None))
+
+    def shared_frame_error(self, ptr: int) -> int:
+        e = C.c_uint32()
+        _check(self.lib.rt_cuda_shared_frame_error(C.c_void_p(ptr), C.byref(e)))
+        return int(e.value)
 
     def copy_to_host(self, host_ptr: int, dev_ptr: int, nbytes: int, stream=None) -> None:
         _check(self.lib.rt_cuda_copy_to_host(C.c_void_p(host_ptr), C.c_void_p(dev_ptr), nbytes, C.c_void_p(stream) if stream else None))

@@ -276,6 +276,8 @@ static void walk(const Tree *T, const RtoObject *obj, const float ray[6], Best *
 	float d[3] = {ray[3], ray[4], ray[5]};
 	if (!(n <= 0x1.4f8b58p-17f && n >= -0x1.4f8b58p-17f)) { d[0] /= n; d[1] /= n; d[2] /= n; }
 	float inv[3] = {1.0f / d[0], 1.0f / d[1], 1.0f / d[2]};
+	if (g_fma)      /* rt_device.cuh: walk_inverse() keeps the reciprocals finite for the fma form */
+		for (int k = 0; k < 3; k++) inv[k] = copysignf(fminf(fabsf(inv[k]), 0x1p100f), inv[k]);
 	Best best = {FLT_MAX, -1};
 	int stack[128], sp = 0;
 	float stack_t[128];
@@ -371,6 +373,12 @@ int main(int argc, char **argv)
 
 	size_t nr = (size_t) W * H;
 	float *rays = malloc(sizeof(float) * 6 * nr);
+	if (getenv("SIM_RAYS")) {
+		/* W*H rays (origin xyz, direction xyz, binary32) from a file instead of the camera */
+		FILE *rf = fopen(getenv("SIM_RAYS"), "rb");
+		if (!rf || fread(rays, sizeof(float) * 6, nr, rf) != nr) { fprintf(stderr, "bad SIM_RAYS file\n"); return 2; }
+		fclose(rf);
+	} else
 	for (int j = 0; j < H; j++)
 		for (int i = 0; i < W; i++)
 			rto_camera_ray(&cam, 1.0f - (float) i / (W - 1), 1.0f - (float) j / (H - 1), (float) W / H, rays + 6 * ((size_t) j * W + i));
