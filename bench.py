@@ -501,11 +501,17 @@ class GpuBench:
         self.barrier()
         return self.allmax(e0.elapsed_time(e1)) / steps
 
-    def measure_config(self, name, steps, warmup, sampler=None):
-        """Device-resident measurement of one config: ms per step, Mrays/s, frame hash."""
+    def measure_config(self, name, steps, warmup, sampler=None, min_ms=None):
+        """Device-resident measurement of one config: ms per step, Mrays/s, frame hash.
+        min_ms: lengthen the timed region to at least this long (so that the 50 ms clock
+        sampler sees it): `steps` becomes a lower bound."""
         cfg = CONFIGS[name]
         self.load_scene(cfg)
         step, finish, to_host, rays, launches, my_rays = self.make_step(cfg)
+        if min_ms:
+            est = self.time_steps(step, finish, 5, 3)
+            steps = int(min(max(steps, min_ms / max(est, 1e-3)), 20000))
+            self.launches += launches * 8
         if sampler:
             sampler.window()
         ms = self.time_steps(step, finish, steps, max(warmup, 3))
@@ -607,8 +613,7 @@ def main_gpu(args):
     if name == "3" and not args.no_other_configs:
         names = [c for c in CONFIGS if c != name and (world == 1 or c in MULTI_GPU_CONFIGS)]
         for c in names:
-            n_steps = 5 if c == "5" else 20
-            m, _ = b.measure_config(c, n_steps, 3, sampler if rank == 0 else None)
+            m, _ = b.measure_config(c, 5, 3, sampler if rank == 0 else None, min_ms=300.0)
             others[c] = m
     clocks = sampler.stop() if rank == 0 else None
 

@@ -266,6 +266,8 @@ int rt_cuda_shared_frame_wait(void *dev_ptr, int num_ranks, uint32_t seq, void *
 int rt_cuda_shared_frame_release(void *dev_ptr, uint32_t seq, void *stream);
 int rt_cuda_shared_frame_error(void *dev_ptr, uint32_t *error_out);
 int rt_cuda_copy_to_host(void *host_dst, const void *dev_src, size_t bytes, void *stream);
+/* stream-ordered copy (no wait) between any two addresses, e.g. a consumer draining the shared frame */
+int rt_cuda_copy_async(void *dst, const void *src, size_t bytes, void *stream);
 
 /* The reference's frame scheduler (main.c:324-482) in three calls:
  *   rt_cuda_set_progressive(init_scale, num_columns)   the --init-scale / --threads flags
@@ -315,6 +317,9 @@ uint64_t rt_pixel_key(float px, float py, uint64_t pass_index);
 /* Register-only FP32 issue-rate probe: TFLOP/s of FMA chains (fma=1) or of
  * MUL+ADD pairs (fma=0, the ceiling of the no-contraction exact build). */
 int rt_cuda_debug_fp32_peak(int fma, float *tflops_out);
+/* LBVH scenes, library built with -DRT_COUNT_WALK only (zeros otherwise): internal nodes
+ * visited and primitives tested by the last call that returned statistics. */
+int rt_cuda_debug_walk_counts(uint64_t *nodes, uint64_t *tests);
 /* Bytes of kernel arguments (camera frame, views, sizes) sent host -> device per launch. */
 size_t rt_cuda_param_bytes(void);
 /* Test knob: tau^2 of the sign shortcut in the light-sample sweep (negative =

@@ -193,9 +193,9 @@ static int init_devices(const int *devices, int count)
 			CU(cudaEventCreateWithFlags(&d.stage_copied[k], cudaEventDisableTiming));
 		}
 		for (auto &ev : d.ev) CU(cudaEventCreate(&ev));
-		CU(cudaMalloc(&d.ray_counter, sizeof(unsigned long long)));
+		CU(cudaMalloc(&d.ray_counter, 4 * sizeof(unsigned long long)));     /* [0] rays; [1], [2]: walk counters of the counter build */
 		CU(cudaMalloc(&d.work_counter, RT_WORK_SLOTS * sizeof(unsigned int)));
-		CU(cudaMemset(d.ray_counter, 0, sizeof(unsigned long long)));
+		CU(cudaMemset(d.ray_counter, 0, 4 * sizeof(unsigned long long)));
 		CU(cudaMallocHost(&d.host_rays, sizeof(unsigned long long)));
 		float lut[256];
 		rt_host_byte_lut(lut);
@@ -879,10 +879,9 @@ static int render_pass(const RtCamera *cam, void *fb, int w, int h, const RtRend
 	int rc = pick_traversal(o->traversal, &pl.lbvh);
 	if (rc != RT_OK) return rc;
 	pl.exact = o->variant == RT_VARIANT_EXACT;
-	/* AUTO: the queued kernel for linear-scan scenes (4K scene_0: 2.06 ms against
-	 * 2.20 ms persistent), the plain persistent kernel for LBVH scenes (same speed,
-	 * less shared memory) */
-	pl.queued = (o->kernel == RT_KERNEL_QUEUED || (o->kernel == RT_KERNEL_AUTO && !pl.lbvh)) && o->scale <= 64;   /* tile width is packed into 7 bits */
+	/* AUTO: the queued kernel (4K scene_0: 1.91 ms against 2.20 ms persistent; 100k spheres
+	 * 4K: 53.9 ms against 55.3 ms) */
+	pl.queued = (o->kernel == RT_KERNEL_QUEUED || o->kernel == RT_KERNEL_AUTO) && o->scale <= 64;   /* tile width is packed into 7 bits */
 	pl.persistent = o->kernel == RT_KERNEL_PERSISTENT || o->kernel == RT_KERNEL_AUTO || pl.queued;
 	pl.wavefront = o->kernel == RT_KERNEL_WAVEFRONT;
 	/* the wavefront kernel packs the tile width into 5 bits and a pixel's x, y into 16 bits each */
@@ -979,7 +978,7 @@ static int render_pass(const RtCamera *cam, void *fb, int w, int h, const RtRend
 		if ((rc = select_device(d)) != RT_OK) return rc;
 		cudaStream_t st = use_user_stream ? (cudaStream_t) o->stream : d.stream;
 		if (stats) {
-			CU(cudaMemsetAsync(d.ray_counter, 0, sizeof(unsigned long long), st));
+			CU(cudaMemsetAsync(d.ray_counter, 0, 4 * sizeof(unsigned long long), st));
 			CU(cudaEventRecord(d.ev[0], st));
 		}
 		/* a GPU whose destination frame lives on another GPU renders into its own
@@ -1448,6 +1447,33 @@ extern "C" int rt_cuda_copy_to_host(void *host_dst, const void *dev_src, size_t 
 	cudaStream_t st = stream ? (cudaStream_t) stream : g.dev[0].stream;
 	CU(cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
+	return RT_OK;
+}
+
+/* Stream-ordered copy between any two addresses of the unified address space
+ * (a consumer draining the shared frame on its own stream). */
+extern "C" int rt_cuda_copy_async(void *dst, const void *src, size_t bytes, void *stream)
+{
+	int rc = require_ready();
+	if (rc != RT_OK) return rc;
+	cudaStream_t st = stream ? (cudaStream_t) stream : g.dev[0].stream;
+	CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, st));
+	return RT_OK;
+}
+
+/* Internal LBVH nodes visited and primitives tested by the last call that asked for
+ * statistics (GPU 0).  Zeros unless the library was built with -DRT_COUNT_WALK
+ * (tools/build_variant.sh): the counters cost registers in the hot loop. */
+extern "C" int rt_cuda_debug_walk_counts(uint64_t *nodes, uint64_t *tests)
+{
+	int rc = require_ready();
+	if (rc != RT_OK) return rc;
+	DeviceCtx &d = g.dev[0];
+	if ((rc = select_device(d)) != RT_OK) return rc;
+	unsigned long long h[4] = {0, 0, 0, 0};
+	CU(cudaMemcpy(h, d.ray_counter, sizeof(h), cudaMemcpyDeviceToHost));
+	if (nodes) *nodes = h[1];
+	if (tests) *tests = h[2];
 	return RT_OK;
 }
 

@@ -219,6 +219,7 @@ def load_library() -> C.CDLL:
     L.rt_cuda_shared_frame_wait.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p]
     L.rt_cuda_shared_frame_release.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
     L.rt_cuda_shared_frame_error.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
+    L.rt_cuda_copy_async.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.rt_cuda_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.rt_cuda_debug_set_sweep_threshold.argtypes = [C.c_float]
     L.rt_cuda_debug_set_tile_schedule.argtypes = [C.c_int]
@@ -226,6 +227,7 @@ def load_library() -> C.CDLL:
     L.rt_cuda_gl_update_frame.argtypes = [C.POINTER(RtCamera), C.c_int, C.c_int, C.c_double, C.POINTER(RtRenderOpts), C.POINTER(RtRenderStats)]
     L.rt_cuda_gl_render_frame.argtypes = [C.POINTER(RtCamera), C.c_int, C.c_int, C.POINTER(RtRenderOpts), C.POINTER(RtRenderStats)]
     L.rt_cuda_param_bytes.restype = C.c_size_t
+    L.rt_cuda_debug_walk_counts.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.rt_cuda_set_progressive.argtypes = [C.c_int, C.c_int]
     L.rt_cuda_accum_generation.restype = C.c_uint32
     L.rt_cuda_update_frame.argtypes = [C.POINTER(RtCamera), C.c_void_p, C.c_int, C.c_int, C.c_double, C.POINTER(RtRenderOpts), C.POINTER(RtRenderStats)]
@@ -543,6 +545,9 @@ class Renderer:
     def copy_to_host(self, host_ptr: int, dev_ptr: int, nbytes: int, stream=None) -> None:
         _check(self.lib.rt_cuda_copy_to_host(C.c_void_p(host_ptr), C.c_void_p(dev_ptr), nbytes, C.c_void_p(stream) if stream else None))
 
+    def copy_async(self, dst_ptr: int, src_ptr: int, nbytes: int, stream=None) -> None:
+        _check(self.lib.rt_cuda_copy_async(C.c_void_p(dst_ptr), C.c_void_p(src_ptr), nbytes, C.c_void_p(stream) if stream else None))
+
     # -- the reference's frame loop (main.c:324-482)
     def set_progressive(self, init_scale: int, num_columns: int = 1) -> None:
         _check(self.lib.rt_cuda_set_progressive(init_scale, num_columns))
@@ -623,6 +628,12 @@ class Renderer:
 
     def set_tile_schedule(self, on: bool) -> None:
         _check(self.lib.rt_cuda_debug_set_tile_schedule(1 if on else 0))
+
+    def walk_counts(self):
+        """(internal LBVH nodes visited, primitives tested) of the last call with stats; zeros unless built with -DRT_COUNT_WALK."""
+        a, b = C.c_uint64(), C.c_uint64()
+        _check(self.lib.rt_cuda_debug_walk_counts(C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     def fp32_peak_tflops(self, fma: bool = True) -> float:
         out = C.c_float()

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--tag", default="")
     ap.add_argument("--sizes", default="1920x1080,3840x2160")
     ap.add_argument("--one", action="store_true", help="render the first size with the first kernel three times and exit (for ncu)")
+    ap.add_argument("--counts", default=None, help="counter build (-DRT_COUNT_WALK): write nodes / tests per ray of the last size to this JSON file")
     a = ap.parse_args()
     import torch
 
@@ -59,6 +60,13 @@ def main():
             ts.sort()
             sha = hashlib.sha256(frame.view(-1)[: w * h * 3].cpu().numpy().tobytes()).hexdigest()[:16]
             out[f"{w}x{h}"] = dict(best=round(ts[0], 3), med=round(ts[len(ts) // 2], 3), rays=st["rays"], mrays_s=round(st["rays"] / ts[0] / 1e3, 1), sha=sha)
+            if a.counts:
+                nodes, tests = r.walk_counts()
+                out[f"{w}x{h}"].update(nodes_per_ray=nodes / st["rays"], tests_per_ray=tests / st["rays"])
+                json.dump(dict(workload=f"{a.n} spheres {w}x{h}, kernel {name}", rays=st["rays"], nodes=nodes, tests=tests,
+                               nodes_per_ray=nodes / st["rays"], tests_per_ray=tests / st["rays"],
+                               how="library built with -DRT_COUNT_WALK (tools/build_variant.sh count -DRT_COUNT_WALK=1), tools/lbvh_ab.py --counts"),
+                          open(a.counts, "w"), indent=1)
         print(json.dumps(out), flush=True)
     r.close()
 
