@@ -65,6 +65,7 @@ typedef struct {
 	f4 *leaf_lo, *leaf_hi;
 	float *leaf_w;
 	float emag;
+	int depth;          /* deepest leaf, levels below the root */
 	int global_pad;     /* the product's static rule */
 	float t_slack;
 } Tree;
@@ -165,6 +166,12 @@ static void build(Tree *T, const RtoObject *obj, int n, int global_pad)
 		parent[right >= 0 ? right : (n - 1) + ~right] = i;
 	}
 	parent[0] = -1;
+
+	for (int sl = 0; sl < n && n >= 2; sl++) {
+		int d = 0;
+		for (int cur = parent[(n - 1) + sl]; cur >= 0; cur = parent[cur]) d++;
+		if (d > T->depth) T->depth = d;
+	}
 
 	/* leaf boxes */
 	double mag = 0;
@@ -444,7 +451,7 @@ int main(int argc, char **argv)
 		rays = next;
 		nr = m;
 	}
-	printf("{\"objects\": %d, \"rays\": %ld, \"mismatches\": %ld, \"nodes_per_ray\": %.2f, \"tests_per_ray\": %.3f, \"deepest_stack\": %d, \"rule\": \"%s\"}\n",
-	       n, total_rays, mism, (double) nodes / total_rays, (double) tests / total_rays, deepest, global_pad ? "static pad (product)" : "per-node pad (experiment)");
+	printf("{\"objects\": %d, \"rays\": %ld, \"mismatches\": %ld, \"nodes_per_ray\": %.2f, \"tests_per_ray\": %.3f, \"deepest_stack\": %d, \"tree_depth\": %d, \"rule\": \"%s\"}\n",
+	       n, total_rays, mism, (double) nodes / total_rays, (double) tests / total_rays, deepest, T.depth, global_pad ? "static pad (product)" : "per-node pad (experiment)");
 	return mism != 0;
 }

