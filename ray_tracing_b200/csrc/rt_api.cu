@@ -884,6 +884,12 @@ static int render_pass(const RtCamera *cam, void *fb, int w, int h, const RtRend
 	pl.queued = (o->kernel == RT_KERNEL_QUEUED || o->kernel == RT_KERNEL_AUTO) && o->scale <= 64;   /* tile width is packed into 7 bits */
 	pl.persistent = o->kernel == RT_KERNEL_PERSISTENT || o->kernel == RT_KERNEL_AUTO || pl.queued;
 	pl.wavefront = o->kernel == RT_KERNEL_WAVEFRONT;
+	/* a tree deeper than the shared-memory traversal stacks is walked by the local-stack build
+	 * of the persistent kernel (rt_render.cu: launch_render), whatever was asked for */
+	if (pl.lbvh && g.dev[0].bvh.depth > RT_SMEM_STACK) {
+		pl.queued = pl.wavefront = false;
+		pl.persistent = true;
+	}
 	/* the wavefront kernel packs the tile width into 5 bits and a pixel's x, y into 16 bits each */
 	if (pl.wavefront && (o->scale > 31 || w > 65535 || h > 65535))
 		return fail(RT_ERR_ARG, "RT_KERNEL_WAVEFRONT supports scale <= 31 and frames up to 65535x65535");

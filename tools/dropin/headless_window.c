@@ -19,7 +19,7 @@
 
 #include "gpu_and_windowing.h"
 
-static int win_w, win_h, frames_shown, frames_wanted = 7, key_sent = -1;
+static int win_w, win_h, frames_shown, frames_wanted = 7, key_sent = -1, close_sent;
 static const char *keys = "";
 static Vector3 *last_frame;
 static int last_w, last_h;
@@ -38,7 +38,12 @@ void startup_window_and_opengl_context_or_exit(int window_w, int window_h, const
 int pop_event(double *mouse_x, double *mouse_y)
 {
 	*mouse_x = *mouse_y = 0;
-	if (frames_shown >= frames_wanted) return EVENT_CLOSE;
+	if (frames_shown >= frames_wanted) {
+		/* main() drains the queue until EVENT_EMPTY before it looks at its exit flag (main.c:522-528) */
+		if (close_sent) return EVENT_EMPTY;
+		close_sent = 1;
+		return EVENT_CLOSE;
+	}
 	if (key_sent < frames_shown) {           /* at most one key per frame, before it is rendered */
 		key_sent = frames_shown;
 		if ((size_t) frames_shown < strlen(keys))

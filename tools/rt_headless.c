@@ -10,8 +10,9 @@
  * --threads only selects the column layout to reproduce, it is clamped to 32
  * like MAX_COLUMNS).  Each frame is one update_frame(): one pass at the current
  * scale, accumulated and resolved on the device, scale halving after every
- * pass (main.c:402-403).  --keys replays W/A/S/D presses (main.c:536-558): each
- * moves the camera by 0.5 and invalidates the accumulation.  --dump writes what
+ * pass (main.c:402-403).  --keys replays W/A/S/D presses (main.c:536-558), one
+ * character per frame (anything else = no event): each press moves the camera by
+ * 0.5 and invalidates the accumulation.  --dump writes what
  * screenshot() would (main.c:637-681): (uint8_t)(x*255), flipped vertically,
  * as a PNG (binary PPM if the name ends in .ppm).
  *
@@ -135,15 +136,18 @@ int main(int argc, char **argv)
 	double render_ms = 0, t0 = now_s();
 	for (int f = 0; f < frames; f++) {
 		if ((size_t) f < nkeys) {                                 /* main.c:526-569 */
+			int moved = 1;
 			switch (keys[f]) {
 			case 'W': case 'w': rt_move_camera(RT_UP, 0.5f); break;
 			case 'A': case 'a': rt_move_camera(RT_LEFT, 0.5f); break;
 			case 'S': case 's': rt_move_camera(RT_DOWN, 0.5f); break;
 			case 'D': case 'd': rt_move_camera(RT_RIGHT, 0.5f); break;
-			default: break;
+			default: moved = 0; break;                            /* any other character: no event before this frame */
 			}
-			rt_cuda_accum_reset();                                /* invalidate_accumulation() */
-			scale = init_scale;
+			if (moved) {
+				rt_cuda_accum_reset();                            /* invalidate_accumulation() */
+				scale = init_scale;
+			}
 		}
 		RtCamera cam = rt_camera_snapshot();
 		RtRenderOpts o;
