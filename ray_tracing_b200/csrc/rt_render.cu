@@ -28,11 +28,15 @@ namespace RT_NS {
 
 /* ---------------------------------------------------------------- helpers */
 
+/* fixed part of a block's scene area: byte LUT, sweep lists, direction caches */
+#define RT_SCENE_HEAD_BYTES (256 * sizeof(float) + RT_BLOCK_THREADS + (RT_BLOCK_THREADS / 32) * RT_DIR_CACHE_BYTES)
+
 struct SharedScene {
 	float4 *A;
 	float4 *B;
 	float  *lut;
 	unsigned char *sweep;     /* 32 bytes per warp: lane list of warp_sweep() */
+	float  *dirs;             /* per warp: direction cache of warp_sweep_cached() (RT_DIR_ROW floats per lane) */
 	int2   *runs;             /* type runs of the scene (rt_device.cuh: nearest_linear) */
 	int    *stack;            /* LBVH: this thread's traversal-stack column (rt_device.cuh: SharedStack) */
 };
@@ -45,7 +49,8 @@ __device__ __forceinline__ SharedScene stage_scene(const RtRenderParams &P, unsi
 	SharedScene s;
 	s.lut = reinterpret_cast<float *>(smem);
 	s.sweep = smem + 256 * sizeof(float) + 32 * (threadIdx.x >> 5);
-	s.A = reinterpret_cast<float4 *>(smem + 256 * sizeof(float) + RT_BLOCK_THREADS);
+	s.dirs = reinterpret_cast<float *>(smem + RT_SCENE_HEAD_BYTES - (RT_BLOCK_THREADS / 32) * RT_DIR_CACHE_BYTES) + (threadIdx.x >> 5) * (32 * RT_DIR_ROW);
+	s.A = reinterpret_cast<float4 *>(smem + RT_SCENE_HEAD_BYTES);
 	s.B = s.A + 1;            /* records interleaved: A[2*i], B[2*i] are neighbours (one address per object) */
 	s.stack = reinterpret_cast<int *>(s.A) + threadIdx.x;   /* LBVH scenes stage no objects: the area holds the stacks */
 	s.runs = reinterpret_cast<int2 *>(s.A + (linear ? 2 * P.scene.n : 0));
@@ -287,8 +292,8 @@ __device__ __forceinline__ unsigned warp_step(Path &p, Walk &w, Stack &st, const
 				              surface_of(hh, __ldg(&P.scene.geomA[hh.obj]), __ldg(&P.scene.geomB[hh.obj]), ro, d, point, normal);
 			              });
 	}
-	warp_sweep(p, S.sweep, P.sweep_tau2);
-	if (p.mode == MODE_LAUNCH) path_launch(p, P.scene);
+	warp_sweep_cached(p, S.sweep, S.dirs);
+	if (p.mode == MODE_LAUNCH) path_launch(p, P.scene, S.dirs + (threadIdx.x & 31) * RT_DIR_ROW);
 	return traced;
 }
 
@@ -752,7 +757,7 @@ render_wavefront_kernel(const __grid_constant__ RtRenderParams P)
 {
 	extern __shared__ __align__(16) unsigned char smem[];
 	SharedScene S = stage_scene(P, smem, !LBVH);
-	size_t scene_bytes = 256 * sizeof(float) + RT_BLOCK_THREADS +
+	size_t scene_bytes = RT_SCENE_HEAD_BYTES +
 	                     (LBVH ? sizeof(int) * RT_SMEM_STACK * RT_BLOCK_THREADS
 	                           : 2 * sizeof(float4) * (size_t) P.scene.n + sizeof(int2) * (size_t) P.scene.num_runs);
 	scene_bytes = (scene_bytes + 15) & ~(size_t) 15;
@@ -1024,7 +1029,7 @@ __global__ void probe_div_kernel(uint64_t seed, unsigned per_thread, int lo_exp_
 
 static size_t smem_bytes(const RtRenderParams &P, bool lbvh)
 {
-	return 256 * sizeof(float) + RT_BLOCK_THREADS +
+	return RT_SCENE_HEAD_BYTES +
 	       (lbvh ? sizeof(int) * RT_SMEM_STACK * RT_BLOCK_THREADS      /* traversal stacks */
 	             : 2 * sizeof(float4) * (size_t) P.scene.n + sizeof(int2) * (size_t) P.scene.num_runs);
 }
