@@ -594,6 +594,25 @@ def main_gpu(args):
                        "note": "tiles handed out in image order (no cost-sorted schedule)"}
         r.set_tile_schedule(True)
 
+    # ---- a moving camera: every pose is new, rendered coarse to fine as update_frame() does
+    # (main.c:354, 402-403).  The scale-1 pass of a fresh pose is ordered by the tile costs its
+    # scale-2 pass recorded; compared with the same pass with tiles in image order ----
+    moving = None
+    if world == 1 and cfg["kind"] == "frame" and args.kernel in ("auto", "queued"):
+        def fresh_pose_scale1_ms(schedule):
+            r.set_tile_schedule(schedule)
+            ms = []
+            for i in range(8):
+                cam = host.Camera((5.0 + 0.03 * (i + 1) + (0.5 if schedule else 0.0), 5.0, 5.0), (-1.0, -1.0, -1.0), (0, 1, 0), 30.0)
+                for sc in (8, 4, 2):
+                    r.render_into(cam, local.data_ptr(), W, H, stats=True, scale=sc, pass_index=0, variant=b.variant, kernel=b.kernel)
+                ms.append(r.render_into(cam, local.data_ptr(), W, H, stats=True, scale=1, pass_index=0, variant=b.variant, kernel=b.kernel)["render_ms"])
+            r.set_tile_schedule(True)
+            return float(np.median(ms))
+        seeded, plain = fresh_pose_scale1_ms(True), fresh_pose_scale1_ms(False)
+        moving = {"scale1_ms_seeded_by_scale2": seeded, "scale1_ms_image_order": plain,
+                  "note": "first scale-1 pass of a NEW pose (8 poses, median), preceded by its scale 8, 4, 2 passes as in update_frame(); device time of the pass"}
+
     # ---- the other build of the same kernels, for the record (N=1 only) ----
     other = None
     if world == 1 and cfg["kind"] == "frame":
@@ -696,6 +715,8 @@ def main_gpu(args):
             line["other_variant"] = other
         if unscheduled:
             line["unscheduled"] = unscheduled
+        if moving:
+            line["moving_camera"] = moving
         if world == 1 and not args.no_cpu_baseline:
             try:
                 c = reference_cpu_run(name, steps=1, warmup=0, budget_s=25.0)

@@ -69,11 +69,26 @@ extern "C" const char *rt_cuda_last_error(void) { return g_err; }
 #define RT_MAX_GPUS 16
 #define RT_WORK_SLOTS 8       /* tile counters: launches that may be in flight at once on one GPU */
 
-/* What a tile schedule is valid for: the same pixels at the same cost. */
+/* What the tile costs of a pose are valid for: the same scene seen from the same
+ * camera through the same frame, band and interleave -- at any scale. */
 struct TileKey {
-	int      w, h, scale, ncols, r0, r1, il_n, il_i, lbvh;
+	int      w, h, ncols, r0, r1, il_n, il_i, lbvh;
 	unsigned scene_epoch;
 	RtCamera cam;
+};
+
+/* Longest-tiles-first schedule of the queued kernel (see tile_schedule()). */
+struct TileSched {
+	TileKey       key;
+	bool          have_key = false;
+	unsigned int *cost[2] = {nullptr, nullptr};     /* per-tile largest bounce count, double buffered */
+	unsigned int *order[2] = {nullptr, nullptr};
+	size_t        cost_cap[2] = {0, 0}, order_cap[2] = {0, 0};
+	int           cost_cur = -1, cost_scale = 0, cost_tiles_x = 0, cost_tiles_y = 0;
+	int           order_cur = -1, order_scale = 0, order_from_scale = 0;
+	size_t        order_tiles = 0;
+	cudaEvent_t   fence = nullptr;                  /* after the last launch that touched these buffers */
+	cudaStream_t  last_stream = nullptr;
 };
 
 struct DeviceCtx {
@@ -91,18 +106,13 @@ struct DeviceCtx {
 	/* outputs */
 	void   *fb = nullptr;       size_t fb_bytes = 0;      /* internal framebuffer (host destinations) */
 	float  *accum = nullptr;    size_t accum_bytes = 0;
+	bool    accum_needs_clear = false;    /* zero it on the stream of the next accumulating pass */
 	int     accum_w = 0, accum_h = 0, accum_row0 = 0, accum_rows = 0;
 	unsigned long long *ray_counter = nullptr;
 	unsigned int       *work_counter = nullptr;   /* RT_WORK_SLOTS counters, one per launch in flight */
 	unsigned            launch_seq = 0;
 	unsigned long long *host_rays = nullptr;              /* pinned */
-	/* longest-tiles-first schedule of the queued kernel (see tile_schedule()) */
-	unsigned int *tile_cost = nullptr, *tile_order = nullptr;
-	size_t        tile_capacity = 0;
-	TileKey       order_key;
-	int           order_state = 0;                        /* 0 none, 1 key seen once, 2 order built */
-	bool          order_in_use = false;                   /* tile_order was given to a launch since it was allocated */
-	cudaEvent_t   order_ready = nullptr;
+	TileSched    sched;
 	/* pipelined host read-back: two staging frames + a copy stream */
 	cudaStream_t copy_stream = nullptr;
 	void        *stage[2] = {nullptr, nullptr};
@@ -146,9 +156,9 @@ static void free_device(DeviceCtx &d)
 	cudaFree(d.sky); cudaFree(d.lut);
 	cudaFree(d.fb); cudaFree(d.accum);
 	cudaFree(d.ray_counter); cudaFree(d.work_counter);
-	cudaFree(d.tile_cost); cudaFree(d.tile_order);
-	d.tile_cost = d.tile_order = nullptr; d.tile_capacity = 0; d.order_state = 0; d.order_in_use = false;
-	if (d.order_ready) { cudaEventDestroy(d.order_ready); d.order_ready = nullptr; }
+	for (int k = 0; k < 2; k++) { cudaFree(d.sched.cost[k]); cudaFree(d.sched.order[k]); }
+	if (d.sched.fence) cudaEventDestroy(d.sched.fence);
+	d.sched = TileSched();
 	if (d.host_rays) cudaFreeHost(d.host_rays);
 	for (auto &e : d.ev) if (e) cudaEventDestroy(e);
 	for (int k = 0; k < 2; k++) {
@@ -455,24 +465,21 @@ static int ensure_accum(DeviceCtx &d, int w, int h, int row0, int rows, bool *fr
 	CU(cudaFree(d.accum));
 	d.accum = nullptr;
 	CU(cudaMalloc(&d.accum, need ? need : 4));
-	CU(cudaMemsetAsync(d.accum, 0, need, d.stream));
+	d.accum_needs_clear = true;
 	d.accum_bytes = need;
 	d.accum_w = w; d.accum_h = h; d.accum_row0 = row0; d.accum_rows = rows;
 	return RT_OK;
 }
 
+/* The buffers are zeroed lazily, on the stream the next accumulating pass is
+ * launched on: a reset issued on the library's stream would race with passes a
+ * caller runs on its own stream (opts->stream). */
 extern "C" int rt_cuda_accum_reset(void)
 {
 	g.accum_count = 0.0f;
 	if (!g.ready) return RT_OK;
-	for (int i = 0; i < g.ngpu; i++) {
-		DeviceCtx &d = g.dev[i];
-		if (!d.accum) continue;
-		int rc = select_device(d);
-		if (rc != RT_OK) return rc;
-		CU(cudaMemsetAsync(d.accum, 0, d.accum_bytes, d.stream));
-	}
-	cudaSetDevice(g.dev[0].device);
+	for (int i = 0; i < g.ngpu; i++)
+		if (g.dev[i].accum) g.dev[i].accum_needs_clear = true;
 	return RT_OK;
 }
 
@@ -638,35 +645,39 @@ static int clear_uncovered_owned(void *fb, const PassPlan &pl, int fb_row_offset
  * several microseconds), so whatever tiles are handed out last decide how long
  * the launch drags on after the work has run out (~0.1 ms per launch with tiles
  * in image order: 5 % of a 4K frame, 30 % of one GPU's share of it at 8 GPUs).
- * The interactive loop renders the same pose pass after pass (main.c:354-403),
- * so pass k tells what pass k+1 will cost: the second launch with an unchanged
- * key records the largest bounce count per tile (one atomicMax per non-sky
- * pixel), a counting sort turns that into an order (costly tiles first, image
- * order within a class), and later launches hand tiles out in that order.
+ * What a tile costs is a property of the POSE, not of the pass: the reference's
+ * loop renders a pose at scale 16, 8, 4, 2, 1, 1, ... (main.c:354-403), and a
+ * coarse pass samples the same surfaces as the fine ones.  So every launch of a
+ * pose that is finer than any before it records the largest bounce count per
+ * tile (one atomicMax per non-sky pixel), and every launch is ordered by the
+ * finest costs known so far -- a fine tile takes the cost of the coarse tile
+ * covering it -- with a stable counting sort (costly tiles first, image order
+ * within a class).  Round 1 only ordered a launch after two identical ones, so
+ * a moving camera (a new pose every frame) never got an order; now its scale-1
+ * pass is ordered by what its scale-2 pass saw.
  * Scheduling only -- every pixel is computed by the same code from the same
  * key, so frames are bit-identical with and without it (test_tile_schedule).
  */
 #define RT_ORDER_THREADS 512
-/* Stable counting sort of the tiles by descending cost class, one CTA: thread t
- * owns a contiguous chunk (a multiple of 4 tiles, read as uint4; the cost array
- * is padded with zeros to a multiple of 4). */
-__global__ void __launch_bounds__(RT_ORDER_THREADS) tile_order_kernel(const unsigned int *cost, unsigned int *order, unsigned n)
+/* Stable counting sort of `n` tiles (tiles_x per row) by descending cost class, one
+ * CTA: thread t owns a contiguous chunk.  Tile (tx, ty) takes the cost of tile
+ * (tx >> shift, ty >> shift) of the cost map (cost_tiles_x per row). */
+__global__ void __launch_bounds__(RT_ORDER_THREADS)
+tile_order_kernel(const unsigned int *cost, unsigned int *order, unsigned n, unsigned tiles_x, unsigned cost_tiles_x,
+                  unsigned cost_tiles_y, unsigned shift)
 {
 	__shared__ unsigned cnt[16][RT_ORDER_THREADS];
 	__shared__ unsigned total[16], base[16];
 	const unsigned t = threadIdx.x;
-	const unsigned chunk = (((n + RT_ORDER_THREADS - 1) / RT_ORDER_THREADS) + 3u) & ~3u;
-	const unsigned lo = min(t * chunk, (n + 3u) & ~3u), hi = min(lo + chunk, (n + 3u) & ~3u);
-	const uint4 *c4 = reinterpret_cast<const uint4 *>(cost);
+	const unsigned chunk = (n + RT_ORDER_THREADS - 1) / RT_ORDER_THREADS;
+	const unsigned lo = min(t * chunk, n), hi = min(lo + chunk, n);
+	auto cost_class = [&](unsigned i) {
+		unsigned ty = i / tiles_x, tx = i - ty * tiles_x;
+		unsigned cx = min(tx >> shift, cost_tiles_x - 1u), cy = min(ty >> shift, cost_tiles_y - 1u);
+		return min(__ldg(cost + (size_t) cy * cost_tiles_x + cx), 15u);
+	};
 	for (int b = 0; b < 16; b++) cnt[b][t] = 0;
-#pragma unroll 4
-	for (unsigned i = lo; i < hi; i += 4) {
-		uint4 c = __ldg(c4 + (i >> 2));
-		cnt[min(c.x, 15u)][t]++;
-		if (i + 1 < n) cnt[min(c.y, 15u)][t]++;
-		if (i + 2 < n) cnt[min(c.z, 15u)][t]++;
-		if (i + 3 < n) cnt[min(c.w, 15u)][t]++;
-	}
+	for (unsigned i = lo; i < hi; i++) cnt[cost_class(i)][t]++;
 	__syncthreads();
 	/* exclusive scan over (class descending, thread ascending) */
 	if (t < 16) {
@@ -680,63 +691,87 @@ __global__ void __launch_bounds__(RT_ORDER_THREADS) tile_order_kernel(const unsi
 		for (int b = 15; b >= 0; b--) { base[b] = run; run += total[b]; }
 	}
 	__syncthreads();
-#pragma unroll 4
-	for (unsigned i = lo; i < hi; i += 4) {
-		uint4 c = __ldg(c4 + (i >> 2));
-		unsigned b;
-		b = min(c.x, 15u); order[base[b] + cnt[b][t]++] = i;
-		if (i + 1 < n) { b = min(c.y, 15u); order[base[b] + cnt[b][t]++] = i + 1; }
-		if (i + 2 < n) { b = min(c.z, 15u); order[base[b] + cnt[b][t]++] = i + 2; }
-		if (i + 3 < n) { b = min(c.w, 15u); order[base[b] + cnt[b][t]++] = i + 3; }
+	for (unsigned i = lo; i < hi; i++) {
+		unsigned b = cost_class(i);
+		order[base[b] + cnt[b][t]++] = i;
 	}
 }
 
-/* Decide what this launch does about the schedule; returns 0 = nothing,
- * 1 = record costs (build_tile_order() must follow the launch), 2 = use the order. */
-static int tile_schedule(DeviceCtx &d, const TileKey &key, size_t tiles, RtRenderParams &P, cudaStream_t stream)
+static bool sched_reserve(unsigned int **buf, size_t *cap, size_t need)
 {
+	if (*cap >= need) return true;
+	cudaFree(*buf);          /* waits for everything that may still read it */
+	*buf = nullptr; *cap = 0;
+	if (cudaMalloc(buf, need * sizeof(unsigned)) != cudaSuccess) { cudaGetLastError(); return false; }
+	*cap = need;
+	return true;
+}
+
+/* Decide what this launch does about the schedule: sets P.tile_order (hand the tiles out in this
+ * order) and / or P.tile_cost (record costs).  Returns true when tile_schedule_done() must follow
+ * the launch. */
+static bool tile_schedule(DeviceCtx &d, const TileKey &key, int scale, int tiles_x, int tiles_y, RtRenderParams &P, cudaStream_t stream, int *launches)
+{
+	TileSched &S = d.sched;
 	P.tile_order = nullptr;
 	P.tile_cost = nullptr;
-	if (!g.tile_schedule || tiles < 2048 || tiles >= (1u << 20)) { d.order_state = 0; return 0; }
-	if (d.order_state == 0 || memcmp(&key, &d.order_key, sizeof(TileKey)) != 0) {
-		d.order_key = key;
-		d.order_state = 1;          /* a moving camera never gets past this: no cost */
-		return 0;
+	const size_t tiles = (size_t) tiles_x * tiles_y;
+	if (!g.tile_schedule || tiles >= (1u << 20)) { S.have_key = false; return false; }
+	if (!S.have_key || memcmp(&key, &S.key, sizeof(TileKey)) != 0) {
+		S.key = key;
+		S.have_key = true;
+		S.cost_cur = S.order_cur = -1;      /* a new pose: nothing is known about it */
 	}
-	if (d.order_state == 1) {
-		/* An order that was handed to earlier launches may still be read by one of
-		 * them on another caller stream: never overwrite it.  cudaFree() waits for
-		 * all work on the device, then fresh buffers are used. */
-		if (d.tile_capacity < tiles || d.order_in_use) {
-			d.order_in_use = false;
-			cudaFree(d.tile_cost); cudaFree(d.tile_order);
-			d.tile_cost = d.tile_order = nullptr; d.tile_capacity = 0;
-			if (cudaMalloc(&d.tile_cost, (tiles + 4) * sizeof(unsigned)) != cudaSuccess ||
-			    cudaMalloc(&d.tile_order, tiles * sizeof(unsigned)) != cudaSuccess) {
-				cudaGetLastError();
-				cudaFree(d.tile_cost); d.tile_cost = nullptr;
-				return 0;
+	if (!S.fence && cudaEventCreateWithFlags(&S.fence, cudaEventDisableTiming) != cudaSuccess) return false;
+	/* the buffers are used in stream order; a caller that switches streams waits for the last user */
+	if (S.last_stream != stream && S.last_stream) cudaStreamWaitEvent(stream, S.fence, 0);
+	S.last_stream = stream;
+	bool touched = false;
+
+	/* ---- the order of this launch ---- */
+	if (tiles >= 2048) {
+		const bool exact_costs = S.cost_cur >= 0 && S.cost_scale == scale;
+		if (S.order_cur >= 0 && S.order_scale == scale && S.order_tiles == tiles && (S.order_from_scale == scale || !exact_costs)) {
+			P.tile_order = S.order[S.order_cur];            /* same pose, same scale: keep the order */
+			touched = true;
+		} else if (S.cost_cur >= 0 && S.cost_scale >= scale && S.cost_scale % scale == 0) {
+			int ratio = S.cost_scale / scale, shift = 0;
+			while ((1 << shift) < ratio) shift++;
+			int o = S.order_cur == 0 ? 1 : 0;
+			if ((1 << shift) == ratio && shift <= 4 && sched_reserve(&S.order[o], &S.order_cap[o], tiles)) {
+				tile_order_kernel<<<1, RT_ORDER_THREADS, 0, stream>>>(S.cost[S.cost_cur], S.order[o], (unsigned) tiles, (unsigned) tiles_x,
+				                                                      (unsigned) S.cost_tiles_x, (unsigned) S.cost_tiles_y, (unsigned) shift);
+				(*launches)++;
+				if (cudaGetLastError() == cudaSuccess) {
+					S.order_cur = o; S.order_scale = scale; S.order_from_scale = S.cost_scale; S.order_tiles = tiles;
+					P.tile_order = S.order[o];
+					touched = true;
+				}
 			}
-			d.tile_capacity = tiles;
 		}
-		if (!d.order_ready && cudaEventCreateWithFlags(&d.order_ready, cudaEventDisableTiming) != cudaSuccess) return 0;
-		if (cudaMemsetAsync(d.tile_cost, 0, (tiles + 4) * sizeof(unsigned), stream) != cudaSuccess) return 0;
-		P.tile_cost = d.tile_cost;
-		return 1;
 	}
-	cudaStreamWaitEvent(stream, d.order_ready, 0);     /* the order may have been built on another stream */
-	P.tile_order = d.tile_order;
-	d.order_in_use = true;
-	return 2;
+	/* ---- record, when this launch sees the pose finer than any launch before it ---- */
+	if (tiles >= 64 && (S.cost_cur < 0 || S.cost_scale > scale)) {
+		int c = S.cost_cur == 0 ? 1 : 0;
+		if (sched_reserve(&S.cost[c], &S.cost_cap[c], tiles) &&
+		    cudaMemsetAsync(S.cost[c], 0, tiles * sizeof(unsigned), stream) == cudaSuccess) {
+			P.tile_cost = S.cost[c];
+			(*launches)++;
+			touched = true;
+		}
+	}
+	return touched;
 }
 
-static int build_tile_order(DeviceCtx &d, size_t tiles, cudaStream_t stream)
+/* after the launch: the recorded costs become the pose's cost map */
+static void tile_schedule_done(DeviceCtx &d, const RtRenderParams &P, int scale, int tiles_x, int tiles_y, cudaStream_t stream)
 {
-	tile_order_kernel<<<1, RT_ORDER_THREADS, 0, stream>>>(d.tile_cost, d.tile_order, (unsigned) tiles);
-	CU(cudaGetLastError());
-	CU(cudaEventRecord(d.order_ready, stream));
-	d.order_state = 2;
-	return RT_OK;
+	TileSched &S = d.sched;
+	if (P.tile_cost) {
+		S.cost_cur = P.tile_cost == S.cost[0] ? 0 : 1;
+		S.cost_scale = scale; S.cost_tiles_x = tiles_x; S.cost_tiles_y = tiles_y;
+	}
+	cudaEventRecord(S.fence, stream);
 }
 
 /* Launch one pass for one device over output rows [r0, r1) (scale aligned). */
@@ -825,23 +860,18 @@ static int launch_band(DeviceCtx &d, const RtCamera *cam, const PassPlan &pl, co
 			unsigned blocks_needed = (warps_needed + (RT_BLOCK_THREADS / 32) - 1) / (RT_BLOCK_THREADS / 32);
 			grid = (int) std::min<unsigned>((unsigned) (d.sm_count * per_sm), blocks_needed);
 		}
-		int sched = 0;
-		size_t tiles = (size_t) P.tiles_x * P.tiles_y;
+		bool sched = false;
 		if (pl.queued) {
 			TileKey key;
 			memset(&key, 0, sizeof(key));
-			key.w = pl.w; key.h = pl.h; key.scale = pl.scale; key.ncols = pl.ncols; key.r0 = r0; key.r1 = r1;
+			key.w = pl.w; key.h = pl.h; key.ncols = pl.ncols; key.r0 = r0; key.r1 = r1;
 			key.il_n = P.il_n; key.il_i = P.il_i; key.lbvh = pl.lbvh; key.scene_epoch = g.scene_epoch;
 			key.cam.pos = cam->pos; key.cam.front = cam->front; key.cam.up = cam->up; key.cam.fov = cam->fov;
-			sched = tile_schedule(d, key, tiles, P, stream);
+			sched = tile_schedule(d, key, pl.scale, P.tiles_x, P.tiles_y, P, stream, launches);
 		}
 		CU((pl.exact ? rt_exact_launch_render : rt_fast_launch_render)(&P, pl.lbvh, pl.queued ? 3 : (pl.persistent ? 1 : 0), grid, stream));
 		(*launches)++;
-		if (sched == 1) {
-			int rc = build_tile_order(d, tiles, stream);
-			if (rc != RT_OK) return rc;
-			(*launches)++;
-		}
+		if (sched) tile_schedule_done(d, P, pl.scale, P.tiles_x, P.tiles_y, stream);
 		}
 	}
 
@@ -1006,6 +1036,11 @@ static int render_pass(const RtCamera *cam, void *fb, int w, int h, const RtRend
 			render_to = d.fb;
 		}
 		int il_i = ngpu > 1 ? i : il_base;
+		if (accumulate && d.accum_needs_clear) {
+			CU(cudaMemsetAsync(d.accum, 0, d.accum_bytes, st));
+			d.accum_needs_clear = false;
+			launches++;
+		}
 		rc = launch_band(d, cam, pl, o, render_to, fb_row_offset, pl.row0, pl.row1, il_n, il_i, st,
 		                 accumulate, wgt, inv, &launches);
 		if (rc != RT_OK) return rc;
@@ -1498,7 +1533,7 @@ extern "C" int rt_cuda_debug_set_sweep_threshold(float tau2)
 extern "C" int rt_cuda_debug_set_tile_schedule(int on)
 {
 	g.tile_schedule = on ? 1 : 0;
-	for (int i = 0; i < g.ngpu; i++) g.dev[i].order_state = 0;
+	for (int i = 0; i < g.ngpu; i++) g.dev[i].sched.have_key = false;
 	return RT_OK;
 }
 

@@ -271,7 +271,11 @@ static float far3(float a, float b, float c, float d)
 	return fmax2(fmax2(fabsf(a), fabsf(b)), fmax2(fabsf(c), fabsf(d)));
 }
 
-static void walk(const Tree *T, const RtoObject *obj, const float ray[6], Best *out, long *nodes, long *tests, int *deepest)
+/* anyhit_light >= 0: shadow-ray mode (rt_device.cuh: the only object whose emission is not zero is
+ * `anyhit_light`): the light is tested first, then the walk only has to find ANY other object
+ * in front of it (or tying with a lower index) and stops there.  out->obj = the light if it is
+ * the nearest hit, otherwise -2 (occluded) or -1 (the light is not hit: nothing to add). */
+static void walk(const Tree *T, const RtoObject *obj, const float ray[6], Best *out, long *nodes, long *tests, int *deepest, int anyhit_light)
 {
 	/* the primitive test is the oracle's own: one-object scan (which normalises
 	 * the direction exactly as trace_ray does, scene.c:158) */
@@ -286,6 +290,13 @@ static void walk(const Tree *T, const RtoObject *obj, const float ray[6], Best *
 	if (g_fma)      /* rt_device.cuh: walk_inverse() keeps the reciprocals finite for the fma form */
 		for (int k = 0; k < 3; k++) inv[k] = copysignf(fminf(fabsf(inv[k]), 0x1p100f), inv[k]);
 	Best best = {FLT_MAX, -1};
+	if (anyhit_light >= 0) {
+		(*tests)++;
+		rto_trace_many(&obj[anyhit_light], 1, ray, 1, out7, &hit);
+		if (hit < 0) { *out = best; return; }
+		best.t = out7[0];
+		best.obj = anyhit_light;
+	}
 	int stack[128], sp = 0;
 	float stack_t[128];
 	int pop_cull = getenv("SIM_POP_CULL") != NULL;
@@ -296,11 +307,15 @@ static void walk(const Tree *T, const RtoObject *obj, const float ray[6], Best *
 			int code = ~node, slot0 = code & ((1 << 27) - 1), cnt = (code >> 27) + 1;
 			for (int k = 0; k < cnt; k++) {
 				int p = T->prim[slot0 + k];
+				if (p == anyhit_light) continue;
 				(*tests)++;
 				rto_trace_many(&obj[p], 1, ray, 1, out7, &hit);
 				if (hit >= 0) {
 					float t = out7[0];
-					if (t < best.t || (t == best.t && p < best.obj)) { best.t = t; best.obj = p; }
+					if (t < best.t || (t == best.t && p < best.obj)) {
+						if (anyhit_light >= 0) { out->t = t; out->obj = -2; return; }
+						best.t = t; best.obj = p;
+					}
 				}
 			}
 		} else {
@@ -391,23 +406,29 @@ int main(int argc, char **argv)
 			rto_camera_ray(&cam, 1.0f - (float) i / (W - 1), 1.0f - (float) j / (H - 1), (float) W / H, rays + 6 * ((size_t) j * W + i));
 
 	long total_rays = 0, mism = 0, nodes = 0, tests = 0;
+	unsigned char *is_shadow = NULL;
+	int anyhit = getenv("SIM_ANYHIT") != NULL;      /* light samples in any-hit mode */
 	int deepest = 0;
 	uint64_t rng = 0x1234;
 	for (int g = 0; g <= gens && nr > 0; g++) {
 		float *out7 = malloc(sizeof(float) * 7 * nr);
 		int32_t *hit = malloc(sizeof(int32_t) * nr);
 		Best *bv = malloc(sizeof(Best) * nr);
-		long gn = 0, gt = 0, gm = 0;
+		long gn = 0, gt = 0, gm = 0, sn = 0, ns = 0;
 		int gd = 0;
-#pragma omp parallel for schedule(dynamic, 64) reduction(+ : gn, gt, gm) reduction(max : gd)
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : gn, gt, gm, sn, ns) reduction(max : gd)
 		for (size_t r = 0; r < nr; r++) {
 			rto_trace_many(obj, n, rays + 6 * r, 1, out7 + 7 * r, hit + r);
 			long a = 0, b = 0;
 			int d = 0;
-			walk(&T, obj, rays + 6 * r, &bv[r], &a, &b, &d);
+			int shadow_mode = anyhit && is_shadow && is_shadow[r];
+			walk(&T, obj, rays + 6 * r, &bv[r], &a, &b, &d, shadow_mode ? light : -1);
 			gn += a; gt += b;
+			if (shadow_mode) { sn += a; ns++; }
 			if (d > gd) gd = d;
 			int ok = bv[r].obj == hit[r] && (hit[r] < 0 || bv[r].t == out7[7 * r]);
+			if (shadow_mode)        /* all that matters: is the light the nearest hit? */
+				ok = (bv[r].obj == light) == (hit[r] == light) && (hit[r] != light || bv[r].t == out7[7 * r]);
 			if (!ok) {
 				gm++;
 				if (gm <= 3) fprintf(stderr, "MISMATCH gen %d ray %zu: scan obj %d t %a, lbvh obj %d t %a\n", g, r, hit[r], out7[7 * r], bv[r].obj, bv[r].t);
@@ -415,10 +436,13 @@ int main(int argc, char **argv)
 		}
 		total_rays += nr; nodes += gn; tests += gt; mism += gm;
 		if (gd > deepest) deepest = gd;
-		fprintf(stderr, "gen %d: %zu rays, %.1f nodes/ray, %.2f tests/ray, %ld mismatches\n", g, nr, (double) gn / nr, (double) gt / nr, gm);
+		fprintf(stderr, "gen %d: %zu rays, %.1f nodes/ray, %.2f tests/ray, %ld mismatches", g, nr, (double) gn / nr, (double) gt / nr, gm);
+		if (ns) fprintf(stderr, "; %ld shadow rays in any-hit mode: %.1f nodes/ray", ns, (double) sn / ns);
+		fprintf(stderr, "\n");
 		/* next generation: a light sample and a bounce from every hit */
 		size_t cap = 2 * nr, m = 0;
 		float *next = malloc(sizeof(float) * 6 * cap);
+		unsigned char *next_shadow = calloc(cap, 1);
 		for (size_t r = 0; r < nr; r++) {
 			if (hit[r] < 0) continue;
 			const float *h = out7 + 7 * r;
@@ -429,6 +453,7 @@ int main(int argc, char **argv)
 				float sd[3], len = 0;
 				for (int k = 0; k < 3; k++) { sd[k] = rd[k] * 0.5f + (lp[k] - pt[k]); len += sd[k] * sd[k]; }
 				len = sqrtf(len);
+				next_shadow[m] = 1;
 				float *q = next + 6 * m++;
 				for (int k = 0; k < 3; k++) { sd[k] /= len; q[k] = pt[k] + sd[k] * 0.001f; q[3 + k] = sd[k]; }
 			}
@@ -447,8 +472,9 @@ int main(int argc, char **argv)
 				}
 			}
 		}
-		free(rays); free(out7); free(hit); free(bv);
+		free(rays); free(out7); free(hit); free(bv); free(is_shadow);
 		rays = next;
+		is_shadow = next_shadow;
 		nr = m;
 	}
 	printf("{\"objects\": %d, \"rays\": %ld, \"mismatches\": %ld, \"nodes_per_ray\": %.2f, \"tests_per_ray\": %.3f, \"deepest_stack\": %d, \"tree_depth\": %d, \"rule\": \"%s\"}\n",

@@ -501,10 +501,11 @@ def test_4k_properties(renderer, port, real_sky, builtin_objects):
 
 
 def test_tile_schedule_changes_nothing(renderer, port, small_sky, builtin_objects):
-    """The queued kernel hands a pose's tiles out longest-first from the third
-    launch on (costs recorded by the second).  Scheduling only: every launch of the
-    sequence -- natural order, recording, reordered -- equals the oracle, with and
-    without interleaving, and leaves no pixel of a sentinel-filled frame behind."""
+    """The queued kernel hands a pose's tiles out longest-first, by the bounce counts
+    the finest earlier launch of that pose recorded (a coarser pass seeds a finer
+    one).  Scheduling only: every launch of the sequence -- natural order, recording,
+    reordered -- equals the oracle, with and without interleaving, and leaves no
+    pixel of a sentinel-filled frame behind."""
     import torch
 
     W, H = 640, 360                       # 7200 tiles: above the scheduling threshold
@@ -525,6 +526,17 @@ def test_tile_schedule_changes_nothing(renderer, port, small_sky, builtin_object
         frame.fill_(-1.0)
         st = renderer.render_into(Camera(), frame.data_ptr(), W, H, stats=True, scale=1, pass_index=5, kernel=RT_KERNEL_QUEUED)
         assert np.array_equal(bits(frame.cpu().numpy()), bits(want5)) and st["rays"] == rays5
+        # a new pose rendered the way update_frame() does, coarse to fine: every pass is
+        # ordered by what the pass before it saw (a fine tile takes its coarse tile's cost)
+        cam2 = Camera((4.0, 4.5, 6.0), (-1.0, -0.8, -1.2), (0, 1, 0), 30.0)
+        W2, H2 = 1280, 720                # scale 4: 4050 tiles, above the ordering threshold from there on
+        world2 = port.world(builtin_objects[0], small_sky, cam2.as_dict())
+        big = torch.empty((H2, W2, 3), dtype=torch.float32, device="cuda")
+        for p_idx, s in enumerate((16, 8, 4, 2, 1, 1)):
+            big.fill_(-1.0)
+            st = renderer.render_into(cam2, big.data_ptr(), W2, H2, stats=True, scale=s, pass_index=p_idx, kernel=RT_KERNEL_QUEUED)
+            w2, r2 = port.render(world2, W2, H2, s, 1, p_idx)
+            assert np.array_equal(bits(big.cpu().numpy()), bits(w2)) and st["rays"] == r2, (s, p_idx)
         # interleaved row blocks: each rank's launches build their own order
         full = want
         for rep in range(3):
