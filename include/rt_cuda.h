@@ -155,6 +155,9 @@ int  rt_cuda_num_gpus(void);
  * LBVH whose hits tie-break by primitive index (== the reference's linear scan). */
 int  rt_cuda_upload_scene(const RtScene *scene);
 int  rt_cuda_upload_objects(const RtObject *objects, int num_objects);
+/* The same objects changed in place (same count, same types in the same order): refresh the
+ * device records and refit the LBVH (topology kept) instead of rebuilding it. */
+int  rt_cuda_update_objects(const RtObject *objects, int num_objects);
 int  rt_cuda_upload_skybox(const RtCubemap *sky);
 
 #define RT_LBVH_THRESHOLD 64

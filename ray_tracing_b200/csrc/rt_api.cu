@@ -340,6 +340,56 @@ extern "C" int rt_cuda_upload_objects(const RtObject *objects, int n)
 	return RT_OK;
 }
 
+/* Objects changed in place (moved, resized, re-coloured; same count, same types in
+ * the same order): refresh the device records and REFIT the LBVH instead of
+ * rebuilding it (~1 ms instead of ~20 ms for 100 000 spheres). */
+extern "C" int rt_cuda_update_objects(const RtObject *objects, int n)
+{
+	int rc = require_ready();
+	if (rc != RT_OK) return rc;
+	if (!g.have_scene) return fail(RT_ERR_STATE, "no scene uploaded (rt_cuda_upload_objects)");
+	if (n != g.n || (n > 0 && !objects)) return fail(RT_ERR_ARG, "rt_cuda_update_objects: %d objects, the uploaded scene has %d", n, g.n);
+	std::vector<int2> runs;
+	for (int i = 0; i < n;) {
+		int ty = (int) objects[i].type, j = i + 1;
+		while (j < n && (int) objects[j].type == ty && j - i < 0xffffff) j++;
+		runs.push_back(make_int2(i, (j - i) | ((ty & 0x7f) << 24)));
+		i = j;
+	}
+	if ((int) runs.size() != g.num_runs) return fail(RT_ERR_ARG, "rt_cuda_update_objects: object types changed; upload the scene again");
+	RtPackedScene ps;
+	rc = rt_host_pack_scene(objects, n, &ps);
+	if (rc != RT_OK) return fail(rc, "out of host memory packing %d objects", n);
+	size_t cnt = n > 0 ? (size_t) n : 1;
+	g.scene_epoch++;                      /* tile costs of the old positions are void */
+	for (int i = 0; i < g.ngpu; i++) {
+		DeviceCtx &d = g.dev[i];
+		if ((rc = select_device(d)) != RT_OK) { rt_host_free_packed(&ps); return rc; }
+		cudaError_t e;
+		if ((e = cudaStreamSynchronize(d.stream)) != cudaSuccess ||
+		    (e = cudaMemcpy(d.geomA, ps.geomA, cnt * sizeof(float4), cudaMemcpyHostToDevice)) != cudaSuccess ||
+		    (e = cudaMemcpy(d.geomB, ps.geomB, cnt * sizeof(float4), cudaMemcpyHostToDevice)) != cudaSuccess ||
+		    (e = cudaMemcpy(d.mat, ps.mat, cnt * RT_MAT_STRIDE * sizeof(float4), cudaMemcpyHostToDevice)) != cudaSuccess ||
+		    (!runs.empty() && (e = cudaMemcpy(d.runs, runs.data(), sizeof(int2) * runs.size(), cudaMemcpyHostToDevice)) != cudaSuccess)) {
+			rt_host_free_packed(&ps);
+			g.have_scene = false;
+			return fail(RT_ERR_CUDA, "scene update: %s", cudaGetErrorString(e));
+		}
+		if (g.have_bvh && (rc = rt_lbvh_update(&d.bvh, d.geomA, d.geomB, &ps, d.stream)) != RT_OK) {
+			rt_host_free_packed(&ps);
+			g.have_scene = false;
+			return fail(rc, "LBVH refit failed: %s", rt_lbvh_last_error());
+		}
+	}
+	g.light_index = ps.light_index;
+	g.light_pos = ps.light_pos;
+	g.div_safe = ps.div_safe;
+	rt_host_free_packed(&ps);
+	if (g.scene_cache) g.scene_cache->num_objects = -1;      /* render_frame_cuda(scene, ...) compares afresh */
+	cudaSetDevice(g.dev[0].device);
+	return RT_OK;
+}
+
 extern "C" int rt_cuda_upload_scene(const RtScene *scene)
 {
 	if (!scene) return fail(RT_ERR_ARG, "scene is NULL");

@@ -270,6 +270,33 @@ int rt_lbvh_refit(RtLbvh *bvh, const float4 *geomA, const float4 *geomB, float d
 	return RT_OK;
 }
 
+__global__ void gather_leaves_kernel(const int *prim_index, int n, const float4 *A, const float4 *B, float4 *leafA, float4 *leafB)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	int p = prim_index[i];
+	leafA[i] = A[p];
+	leafB[i] = B[p];
+}
+
+/* Objects moved (same count): keep the topology, refresh the leaf records and refit
+ * every box bottom-up.  The tree stays correct for any motion -- the boxes are
+ * recomputed from the new primitives -- but its quality degrades with large
+ * displacements; rebuild (rt_cuda_upload_objects) when that matters. */
+int rt_lbvh_update(RtLbvh *bvh, const float4 *geomA, const float4 *geomB, const RtPackedScene *hs, cudaStream_t stream)
+{
+	int n = bvh->num_prims;
+	if (n <= 0) return RT_OK;
+	if (hs->n != n) return lfail(RT_ERR_ARG, "LBVH update: %d objects, the tree was built for %d", hs->n, n);
+	bvh->lo = hs->bounds_lo;
+	bvh->hi = hs->bounds_hi;
+	gather_leaves_kernel<<<(n + 255) / 256, 256, 0, stream>>>(bvh->prim_index, n, geomA, geomB, bvh->leafA, bvh->leafB);
+	LCU(cudaGetLastError());
+	float d_max = rt_lbvh_default_dmax((double) hs->bounds_hi.x - hs->bounds_lo.x, (double) hs->bounds_hi.y - hs->bounds_lo.y,
+	                                   (double) hs->bounds_hi.z - hs->bounds_lo.z);
+	return rt_lbvh_refit(bvh, geomA, geomB, d_max, stream);
+}
+
 int rt_lbvh_build(RtLbvh *bvh, const float4 *geomA, const float4 *geomB, int n,
                   const RtPackedScene *hs, cudaStream_t stream)
 {

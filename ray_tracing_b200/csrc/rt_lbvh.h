@@ -32,6 +32,7 @@ int  rt_lbvh_build(RtLbvh *bvh, const float4 *geomA, const float4 *geomB, int n,
  * (topology unchanged).  Called when the camera leaves the region the build
  * assumed. */
 int  rt_lbvh_refit(RtLbvh *bvh, const float4 *geomA, const float4 *geomB, float d_max, cudaStream_t stream);
+int  rt_lbvh_update(RtLbvh *bvh, const float4 *geomA, const float4 *geomB, const RtPackedScene *host_scene, cudaStream_t stream);
 void rt_lbvh_free(RtLbvh *bvh);
 RtBvhView rt_lbvh_view(const RtLbvh *bvh);
 const char *rt_lbvh_last_error(void);

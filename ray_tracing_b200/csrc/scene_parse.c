@@ -257,15 +257,14 @@ typedef struct {
 	int       growable;
 } Sink;
 
-static int parse_all(const char *src, size_t len, Sink *sink)
+/* Parse every object in c->s[c->i .. c->n) and append it to the sink. */
+static int parse_objects(Cursor *c, Sink *sink)
 {
-	Cursor c = {src, len, 0, 1};
-	sink->count = 0;
 	for (;;) {
-		skip_blanks(&c);
-		if (c.i >= c.n) return 1;
+		skip_blanks(c);
+		if (c->i >= c->n) return 1;
 		RtObject o;
-		if (!one_object(&c, &o)) return 0;
+		if (!one_object(c, &o)) return 0;
 		if (sink->count == sink->cap && sink->growable) {
 			int ncap = sink->cap ? sink->cap * 2 : 1024;
 			RtObject *p = (RtObject *) realloc(sink->items, (size_t) ncap * sizeof(RtObject));
@@ -278,7 +277,7 @@ static int parse_all(const char *src, size_t len, Sink *sink)
 			sink->cap = ncap;
 		}
 		if (sink->count == sink->cap)
-			fprintf(stderr, "Warning: Ignoring object because the scene is too big (line %d)\n", c.line);
+			fprintf(stderr, "Warning: Ignoring object because the scene is too big (line %d)\n", c->line);
 		else {
 			/* assign field-wise what the reference assigns; the sphere's union
 			 * tail stays whatever the destination held */
@@ -289,6 +288,70 @@ static int parse_all(const char *src, size_t len, Sink *sink)
 			d->material = o.material;
 		}
 	}
+}
+
+static int parse_all(const char *src, size_t len, Sink *sink)
+{
+	Cursor c = {src, len, 0, 1};
+	sink->count = 0;
+	return parse_objects(&c, sink);
+}
+
+/*
+ * Streaming variant for large files (the 100 000-sphere scene is
+ * 15 MB of text; the reference reads a whole file into memory, utils.c:32-58 +
+ * scene.c:611-624).  The file is read through a window of RT_PARSE_WINDOW bytes
+ * that is cut at the last object keyword it holds: no property keyword and no
+ * number contains "sphere" or "cube", so in a well-formed file a blank followed
+ * by one of them starts an object and everything before it is complete objects.
+ * The tail moves to the front of the window and the next read appends to it.
+ * Line numbers in messages carry across windows.
+ */
+#define RT_PARSE_WINDOW (1u << 20)
+
+static size_t last_object_start(const char *s, size_t n)
+{
+	for (size_t i = n; i-- > 1;) {
+		if (!blank(s[i - 1])) continue;
+		if ((n - i >= 6 && memcmp(s + i, "sphere", 6) == 0) || (n - i >= 4 && memcmp(s + i, "cube", 4) == 0)) return i;
+	}
+	return 0;
+}
+
+static int parse_stream(FILE *f, Sink *sink)
+{
+	size_t cap = RT_PARSE_WINDOW, have = 0;
+	char *buf = (char *) malloc(cap + 1);
+	int line = 1, ok = 1;
+	sink->count = 0;
+	if (!buf) {
+		fprintf(stderr, "Error: out of memory while parsing scene\n");
+		return 0;
+	}
+	for (;;) {
+		size_t got = fread(buf + have, 1, cap - have, f);
+		have += got;
+		int eof = got == 0;
+		size_t cut = eof ? have : last_object_start(buf, have);
+		if (!eof && cut == 0) {
+			/* one object larger than the window (or no keyword yet): grow and read on */
+			if (have == cap) {
+				char *p = (char *) realloc(buf, 2 * cap + 1);
+				if (!p) { fprintf(stderr, "Error: out of memory while parsing scene\n"); ok = 0; break; }
+				buf = p;
+				cap *= 2;
+			}
+			continue;
+		}
+		Cursor c = {buf, cut, 0, line};
+		ok = parse_objects(&c, sink);
+		line = c.line;
+		if (!ok || eof) break;
+		memmove(buf, buf + cut, have - cut);
+		have -= cut;
+	}
+	free(buf);
+	return ok;
 }
 
 static char *slurp(const char *file, size_t *len)
@@ -346,17 +409,24 @@ int rt_parse_scene_string_large(const char *src, size_t len, RtObject **objects,
 
 int rt_parse_scene_file_large(const char *file, RtObject **objects, int *num_objects)
 {
-	size_t len = 0;
-	char *src = slurp(file, &len);
-	if (!src) {
+	*objects = NULL;
+	*num_objects = 0;
+	FILE *f = fopen(file, "rb");
+	if (!f) {
 		fprintf(stderr, "Error: Couldn't open scene file\n");
-		*objects = NULL;
-		*num_objects = 0;
 		return RT_ERR_IO;
 	}
-	int rc = rt_parse_scene_string_large(src, len, objects, num_objects);
-	free(src);
-	return rc;
+	Sink sink = {NULL, 0, 0, 1};
+	int ok = parse_stream(f, &sink);
+	int io_error = ferror(f);
+	fclose(f);
+	if (!ok || io_error) {
+		free(sink.items);
+		return io_error ? RT_ERR_IO : RT_ERR_PARSE;
+	}
+	*objects = sink.items;
+	*num_objects = sink.count;
+	return RT_OK;
 }
 
 void rt_free_objects(RtObject *objects) { free(objects); }

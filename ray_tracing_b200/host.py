@@ -199,6 +199,7 @@ def load_library() -> C.CDLL:
     L.rt_cuda_shutdown.restype = None
     L.rt_cuda_upload_scene.argtypes = [C.POINTER(RtScene)]
     L.rt_cuda_upload_objects.argtypes = [C.c_void_p, C.c_int]
+    L.rt_cuda_update_objects.argtypes = [C.c_void_p, C.c_int]
     L.rt_cuda_upload_skybox.argtypes = [C.POINTER(RtCubemap)]
     L.rt_render_opts_default.argtypes = [C.POINTER(RtRenderOpts)]
     L.rt_render_opts_default.restype = None
@@ -438,6 +439,11 @@ class Renderer:
         objects = np.ascontiguousarray(objects, dtype=OBJECT_DTYPE)
         _check(self.lib.rt_cuda_upload_objects(objects.ctypes.data, len(objects)))
 
+    def update_objects(self, objects) -> None:
+        """Same objects, changed in place: refresh device records, refit the LBVH (no rebuild)."""
+        objects = np.ascontiguousarray(objects, dtype=OBJECT_DTYPE)
+        _check(self.lib.rt_cuda_update_objects(objects.ctypes.data, len(objects)))
+
     def upload_skybox(self, faces: np.ndarray) -> None:
         """faces: (6, h, w, chan>=3) uint8 in CubeFace order (front, back, left,
         right, top, bottom), rows top first -- what stb_image returns."""
@@ -621,6 +627,13 @@ class Renderer:
         st = RtRenderStats()
         cam = camera.as_struct()
         _check(self.lib.rt_cuda_gl_update_frame(C.byref(cam), w, h, budget_ms, C.byref(o), C.byref(st)))
+        return _stats_dict(st)
+
+    def gl_render_frame(self, camera: Camera, w: int, h: int, **opts):
+        o = self._opts(**opts)
+        st = RtRenderStats()
+        cam = camera.as_struct()
+        _check(self.lib.rt_cuda_gl_render_frame(C.byref(cam), w, h, C.byref(o), C.byref(st)))
         return _stats_dict(st)
 
     def gl_unregister_buffer(self) -> None:

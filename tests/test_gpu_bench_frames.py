@@ -163,3 +163,40 @@ def test_lbvh_fuzz_near_and_far_cameras(renderer, port, small_sky, seed, n, exte
         frame, st = renderer.render_frame(c, 200, 112, 1, kernel=kern)
         assert np.array_equal(frame.view(np.uint32), want.view(np.uint32)), (seed, kern)
         assert st["rays"] == rays
+
+
+def test_refit_after_moving_objects_equals_oracle(renderer, port, small_sky):
+    """rt_cuda_update_objects: 1 % of the spheres of a 20 000-sphere scene move (some
+    far outside the old bounds), the LBVH is refitted, not rebuilt; frames equal the O(N) oracle on the
+    moved scene and a fresh upload of it."""
+    import time
+
+    from conftest import random_scene
+
+    objs = random_scene(20000, seed=21, spheres_only=True, extent=25.0)
+    renderer.upload_skybox(small_sky)
+    renderer.upload_scene(objs)
+    cam = Camera((3.0, 4.0, 2.0), (-1.0, -0.5, -0.8), (0, 1, 0), 30.0)
+    before, _ = renderer.render_frame(cam, 200, 112, 1)
+    rng = np.random.default_rng(5)
+    moved = objs.copy()
+    idx = rng.choice(len(objs), len(objs) // 100, replace=False)
+    moved["geom"][idx, :3] += np.round(rng.normal(scale=4.0, size=(len(idx), 3)), 3).astype(np.float32)
+    moved["geom"][idx[:5], :3] += 60.0                      # a few leave the old bounds altogether
+    t0 = time.perf_counter()
+    renderer.update_objects(moved)
+    renderer.synchronize()
+    refit_s = time.perf_counter() - t0
+    got, st = renderer.render_frame(cam, 200, 112, 1)
+    want, rays = port.render(port.world(moved, small_sky, cam.as_dict()), 200, 112, 1, 1, 0)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)) and st["rays"] == rays
+    assert not np.array_equal(got, before)
+    t0 = time.perf_counter()
+    renderer.upload_scene(moved)
+    renderer.synchronize()
+    build_s = time.perf_counter() - t0
+    again, _ = renderer.render_frame(cam, 200, 112, 1)
+    assert np.array_equal(again.view(np.uint32), want.view(np.uint32))
+    print(f"refit {refit_s * 1e3:.2f} ms, rebuild {build_s * 1e3:.2f} ms")
+    with pytest.raises(host.RtError):
+        renderer.update_objects(moved[:-1])

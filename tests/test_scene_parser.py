@@ -158,3 +158,26 @@ def test_capacity_and_large_variant(tmp_path):
 def test_partial_count_on_error():
     ok, objs = host.parse_scene_string_partial("sphere\ncube\nsphere radius x")
     assert not ok and len(objs) == 2           # scene.c:208: num_objects keeps what was parsed
+
+
+def test_streaming_file_parser_equals_in_memory_parse(tmp_path):
+    """rt_parse_scene_file_large reads through a 1 MiB window cut at object
+    boundaries; the records must equal those of the in-memory
+    parse of the same text, across several windows, and errors keep their line."""
+    from ray_tracing_b200 import host, scenes
+
+    text = scenes.synthetic_spheres_text(20000, seed=3)            # ~3.6 MB: four windows
+    cubes = "".join(f"cube origin {{{i} 0 {i}}} size {{1 2 3}}\n   albedo   {{0.5 0.25 1}}  roughness 0.5\n" for i in range(3000))
+    text = text[: len(text) // 2].rsplit("sphere", 1)[0] + cubes + text[len(text) // 2:].split("sphere", 1)[1].join(["sphere", ""])
+    path = tmp_path / "big.txt"
+    path.write_text(text)
+    a = host.parse_scene_file_large(str(path))
+    b = host.parse_scene_string_large(text)
+    assert len(a) == len(b) > 20000
+    assert np.array_equal(np.ascontiguousarray(a).view(np.uint8), np.ascontiguousarray(b).view(np.uint8))
+    bad = tmp_path / "bad.txt"
+    lines = text.split("\n")
+    lines[len(lines) * 3 // 4] = "sphere radius x"
+    bad.write_text("\n".join(lines))
+    with pytest.raises(host.RtError):
+        host.parse_scene_file_large(str(bad))
