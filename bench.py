@@ -411,23 +411,27 @@ class GpuBench:
             frame = torch.empty((H, W, 3), dtype=torch.float32, device=self.dev)
             rs = self.render_stream.cuda_stream
 
-            def issue(stats=False):
+            def issue(k, stats=False):
+                # pass k of the pose: the reference's accumulation draws fresh samples every pass (main.c:354-403)
                 if sweep:
-                    _, st = r.render_sweep(cam, W, H, cfg["init_scale"], 0, ptr=frame.data_ptr(), stats=stats, stream=rs, **common)
+                    _, st = r.render_sweep(cam, W, H, cfg["init_scale"], 5 * k, ptr=frame.data_ptr(), stats=stats, stream=rs, **common)
                     return st
-                return r.render_into(cam, frame.data_ptr(), W, H, stats=stats, stream=rs, scale=1, pass_index=0, **common)
+                return r.render_into(cam, frame.data_ptr(), W, H, stats=stats, stream=rs, scale=1, pass_index=k, **common)
 
-            st = issue(stats=True)
+            st = issue(0, stats=True)
             rays = st["rays"]
             launches = st["kernel_launches"]
+            counter = [0]
 
             def step():
-                issue()
+                issue(counter[0])
+                counter[0] += 1
 
             def finish():
                 pass
 
             def to_host():
+                issue(0)                       # the frame that is hashed: pass 0
                 torch.cuda.synchronize()
                 return frame.cpu().numpy()
 
@@ -452,13 +456,18 @@ class GpuBench:
         launches = st["kernel_launches"] + 3       # + arrive flag, ack poll, (rank 0) wait/release
         self.barrier()
 
-        def step():
+        counter = [0]
+
+        def step(k=None):
             shared[1] += 1
             seq = shared[1]
+            if k is None:
+                k = counter[0]
+                counter[0] += 1
             if sweep:
-                r.render_sweep(cam, W, H, cfg["init_scale"], 0, ptr=ptr, stats=False, stream=rs, frame_seq=seq, frame_ack=1, **il, **common)
+                r.render_sweep(cam, W, H, cfg["init_scale"], 5 * k, ptr=ptr, stats=False, stream=rs, frame_seq=seq, frame_ack=1, **il, **common)
             else:
-                r.render_into(cam, ptr, W, H, stream=rs, scale=1, pass_index=0, frame_seq=seq, frame_ack=1, **il, **common)
+                r.render_into(cam, ptr, W, H, stream=rs, scale=1, pass_index=k, frame_seq=seq, frame_ack=1, **il, **common)
             if self.rank == 0:
                 # the consumer: frame seq is whole once every rank's blocks have landed; hand it back at once
                 r.shared_frame_wait(ptr, self.world, seq, stream=cs)
@@ -470,6 +479,8 @@ class GpuBench:
                 self.render_stream.wait_stream(self.consumer_stream)
 
         def to_host():
+            step(0)                            # the frame that is hashed: pass 0
+            finish()
             self.barrier()
             r.synchronize()
             self.barrier()
@@ -485,12 +496,15 @@ class GpuBench:
         return step, finish, to_host, rays, launches, my_rays
 
     def time_steps(self, step, finish, steps, warmup):
+        """Returns (ms per step, rays per step): max over ranks of the device time, and the rays the
+        kernels counted over exactly the timed steps (all ranks)."""
         torch = self.torch
         for _ in range(warmup):
             step()
         finish()
         self.r.synchronize()
         self.barrier()
+        rays0 = self.r.ray_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(self.render_stream)
         for _ in range(steps):
@@ -499,7 +513,8 @@ class GpuBench:
         e1.record(self.render_stream)
         self.r.synchronize()
         self.barrier()
-        return self.allmax(e0.elapsed_time(e1)) / steps
+        rays = self.allsum_int(self.r.ray_counter() - rays0)
+        return self.allmax(e0.elapsed_time(e1)) / steps, rays / steps
 
     def measure_config(self, name, steps, warmup, sampler=None, min_ms=None):
         """Device-resident measurement of one config: ms per step, Mrays/s, frame hash.
@@ -509,16 +524,17 @@ class GpuBench:
         self.load_scene(cfg)
         step, finish, to_host, rays, launches, my_rays = self.make_step(cfg)
         if min_ms:
-            est = self.time_steps(step, finish, 5, 3)
+            est, _ = self.time_steps(step, finish, 5, 3)
             steps = int(min(max(steps, min_ms / max(est, 1e-3)), 20000))
             self.launches += launches * 8
         if sampler:
             sampler.window()
-        ms = self.time_steps(step, finish, steps, max(warmup, 3))
+        ms, rays = self.time_steps(step, finish, steps, max(warmup, 3))
         clocks = sampler.window() if sampler else None
         frame = to_host()
         out = dict(config=name, workload=cfg["workload"], ms_per_step=ms, rays_per_step=rays, value=rays / (ms * 1e-3) / 1e6, unit="Mrays/s",
-                   frames_per_s=1e3 / ms, steps=steps, launches_per_step=launches, clocks=clocks)
+                   frames_per_s=1e3 / ms, steps=steps, launches_per_step=launches, clocks=clocks,
+                   passes="step k renders pass k of the pose (fresh samples every pass, as the reference's accumulation); rays_per_step = rays counted by the kernels over the timed steps / steps; the hashed frame is pass 0")
         if self.rank == 0:
             out["frame_sha256"] = sha256_frame(frame)
             want = golden_hash(name, self.sky_desc)
@@ -564,33 +580,42 @@ def main_gpu(args):
     il = dict(interleave_count=world, interleave_index=rank) if world > 1 else {}
     kopts = dict(variant=b.variant, kernel=b.kernel, stream=b.render_stream.cuda_stream, **il)
 
-    def kernel_only():
+    kcount = [0]
+
+    def kernel_only(**over):
+        k = kcount[0]
+        kcount[0] += 1
+        o = dict(kopts, **over)
         if cfg["kind"] == "sweep":
-            r.render_sweep(b.cam, W, H, cfg["init_scale"], 0, ptr=local.data_ptr(), stats=False, **kopts)
+            r.render_sweep(b.cam, W, H, cfg["init_scale"], 5 * k, ptr=local.data_ptr(), stats=False, **o)
         else:
-            r.render_into(b.cam, local.data_ptr(), W, H, scale=1, pass_index=0, **kopts)
+            r.render_into(b.cam, local.data_ptr(), W, H, scale=1, pass_index=k, **o)
 
     def time_local(fn, n):
+        """(ms per launch, rays per launch) of n back-to-back launches on this rank."""
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
+        rays0 = r.ray_counter()
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         k0.record(b.render_stream)
         for _ in range(n):
             fn()
         k1.record(b.render_stream)
         torch.cuda.synchronize()
-        return k0.elapsed_time(k1) / n
+        return k0.elapsed_time(k1) / n, (r.ray_counter() - rays0) / n
 
-    kern_ms = b.allmax(time_local(kernel_only, args.steps))
+    kern_ms_local, kern_rays = time_local(kernel_only, args.steps)
+    kern_ms = b.allmax(kern_ms_local)
+    my_rays = kern_rays
 
     # ---- the same launches with tiles in image order (what a pose costs the first two
     # times it is rendered, and every time while the camera moves), for the record ----
     unscheduled = None
     if args.kernel in ("auto", "queued") and cfg["kind"] == "frame":
         r.set_tile_schedule(False)
-        ums = b.time_steps(step, finish, 10, 3)
-        unscheduled = {"ms_per_step": ums, "value": rays_per_step / (ums * 1e-3) / 1e6, "unit": "Mrays/s",
+        ums, urays = b.time_steps(step, finish, 10, 3)
+        unscheduled = {"ms_per_step": ums, "value": urays / (ums * 1e-3) / 1e6, "unit": "Mrays/s",
                        "note": "tiles handed out in image order (no cost-sorted schedule)"}
         r.set_tile_schedule(True)
 
@@ -617,10 +642,7 @@ def main_gpu(args):
     other = None
     if world == 1 and cfg["kind"] == "frame":
         ov = host.RT_VARIANT_EXACT if not exact else host.RT_VARIANT_FAST
-        oc = dict(kopts, variant=ov)
-        oms = time_local(lambda: r.render_into(b.cam, local.data_ptr(), W, H, scale=1, pass_index=0, **oc), 10)
-        oc.pop("stream")
-        orays = r.render_into(b.cam, local.data_ptr(), W, H, stats=True, scale=1, pass_index=0, **oc)["rays"]
+        oms, orays = time_local(lambda: kernel_only(variant=ov), 10)
         other = {"variant": "exact" if ov == host.RT_VARIANT_EXACT else "fast", "ms_per_step": oms, "value": orays / (oms * 1e-3) / 1e6, "unit": "Mrays/s",
                  "note": "fast = FMA contraction + approximate rcp/rsqrt, f32 sphere roots: <= 1 LSB/8-bit channel on >= 99.9 % of pixels; exact = bit-identical to the reference"}
 

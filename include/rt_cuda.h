@@ -303,6 +303,10 @@ int rt_cuda_gl_update_frame(const RtCamera *cam, int w, int h, double budget_ms,
 int rt_cuda_gl_render_frame(const RtCamera *cam, int w, int h, const RtRenderOpts *opts, RtRenderStats *stats);
 int rt_cuda_gl_unregister_buffer(void);
 
+/* Rays traced on GPU 0 since the last call that returned RtRenderStats (such calls reset the
+ * counter); waits for the device.  Counts a run of asynchronous launches exactly. */
+int rt_cuda_ray_counter(uint64_t *rays);
+
 /* Block until all work issued by the library has finished. */
 int rt_cuda_synchronize(void);
 
@@ -332,6 +336,10 @@ int rt_cuda_debug_set_sweep_threshold(float tau2);
  * repeatedly is scheduled longest tiles first from the costs its previous pass recorded.
  * Scheduling only: frames must be identical either way. */
 int rt_cuda_debug_set_tile_schedule(int on);
+/* Unit probe of the longest-tiles-first order: tiles_x*tiles_y tiles ordered by the costs of a map
+ * that is 1 << shift times coarser (stable: costly classes first, image order within a class). */
+int rt_cuda_debug_tile_order(const uint32_t *cost, int cost_tiles_x, int cost_tiles_y, int shift,
+                             int tiles_x, int tiles_y, uint32_t *order_out);
 /* Bit-compare the render kernels' hoisted-reciprocal division with IEEE `/` on
  * blocks*256*per_thread operand pairs (exponent ranges given); see rt_device.cuh. */
 int rt_cuda_debug_div_check(uint64_t seed, unsigned blocks, unsigned per_thread, int lo_exp_b, int hi_exp_b,

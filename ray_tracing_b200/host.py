@@ -227,6 +227,8 @@ def load_library() -> C.CDLL:
     L.rt_cuda_gl_register_buffer.argtypes = [C.c_uint, C.c_size_t]
     L.rt_cuda_gl_update_frame.argtypes = [C.POINTER(RtCamera), C.c_int, C.c_int, C.c_double, C.POINTER(RtRenderOpts), C.POINTER(RtRenderStats)]
     L.rt_cuda_gl_render_frame.argtypes = [C.POINTER(RtCamera), C.c_int, C.c_int, C.POINTER(RtRenderOpts), C.POINTER(RtRenderStats)]
+    L.rt_cuda_debug_tile_order.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.rt_cuda_ray_counter.argtypes = [C.POINTER(C.c_uint64)]
     L.rt_cuda_param_bytes.restype = C.c_size_t
     L.rt_cuda_debug_walk_counts.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.rt_cuda_set_progressive.argtypes = [C.c_int, C.c_int]
@@ -641,6 +643,18 @@ class Renderer:
 
     def set_tile_schedule(self, on: bool) -> None:
         _check(self.lib.rt_cuda_debug_set_tile_schedule(1 if on else 0))
+
+    def debug_tile_order(self, cost: np.ndarray, shift: int, tiles_x: int, tiles_y: int) -> np.ndarray:
+        cost = np.ascontiguousarray(cost, dtype=np.uint32)
+        out = np.zeros(tiles_x * tiles_y, np.uint32)
+        _check(self.lib.rt_cuda_debug_tile_order(cost.ctypes.data, cost.shape[1], cost.shape[0], shift, tiles_x, tiles_y, out.ctypes.data))
+        return out
+
+    def ray_counter(self) -> int:
+        """Rays traced on GPU 0 since the last call that returned statistics (waits for the device)."""
+        n = C.c_uint64()
+        _check(self.lib.rt_cuda_ray_counter(C.byref(n)))
+        return int(n.value)
 
     def walk_counts(self):
         """(internal LBVH nodes visited, primitives tested) of the last call with stats; zeros unless built with -DRT_COUNT_WALK."""

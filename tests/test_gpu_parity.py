@@ -651,3 +651,19 @@ def test_config5_4k_properties(renderer, small_sky, spheres_100k):
     assert np.array_equal(bits(frame.cpu().numpy()), bits(a)) and rays == sa["rays"]
     assert a.min() >= 0.0 and a.max() <= 1.0
     assert sa["rays"] > 8e7
+
+
+@pytest.mark.parametrize("tx,ty,shift", [(480, 540, 0), (480, 540, 1), (160, 23, 0), (97, 61, 2), (31, 33, 0)])
+def test_tile_order_kernel_is_a_stable_sort_by_descending_cost(renderer, tx, ty, shift):
+    """rt_api.cu: tile_order_kernel against numpy: a permutation of all tiles, costly classes first
+    (costs above 15 share the top class), image order within a class; a fine tile takes the cost of
+    the coarse tile covering it."""
+    rng = np.random.default_rng(tx * 7 + ty + shift)
+    cx, cy = (tx + (1 << shift) - 1) >> shift, (ty + (1 << shift) - 1) >> shift
+    cost = rng.choice([0, 0, 0, 1, 2, 3, 5, 9, 10, 14, 15, 16, 40], size=(cy, cx)).astype(np.uint32)
+    got = renderer.debug_tile_order(cost, shift, tx, ty)
+    i = np.arange(tx * ty)
+    cls = np.minimum(cost[(i // tx) >> shift, (i % tx) >> shift], 15)
+    want = np.argsort(-cls.astype(np.int64), kind="stable").astype(np.uint32)
+    assert np.array_equal(np.sort(got), i)
+    assert np.array_equal(got, want)
