@@ -11,6 +11,7 @@
  * checked on the CPU against the O(N) scan by tests/lbvh_sim.c.
  */
 #include <cub/device/device_radix_sort.cuh>
+#include <cuda_fp16.h>
 
 #include <math.h>
 #include <stdarg.h>
@@ -74,16 +75,26 @@ __global__ void morton_kernel(const float4 *A, const float4 *B, int n, float3 lo
 	keys[i] = ((unsigned long long) code << 32) | (unsigned int) i;
 }
 
-/* sorted keys -> primitive index per leaf slot, and the primitive records in that order */
+/* The record the walk loads for leaf slot i with ONE 32-byte load: geomA of the primitive, then
+ * geomB.xyz and the primitive index with its type in the top two bits. */
+__device__ __forceinline__ void write_leaf(float4 *leaves, int slot, int p, const float4 *A, const float4 *B)
+{
+	float4 a = A[p], b = B[p];
+	int ty = __float_as_int(b.w);
+	ty = ty == RT_OBJECT_CUBE || ty == RT_OBJECT_SPHERE ? ty : 2;
+	leaves[2 * (size_t) slot] = a;
+	leaves[2 * (size_t) slot + 1] = make_float4(b.x, b.y, b.z, __int_as_float(p | (ty << 30)));
+}
+
+/* sorted keys -> primitive index per leaf slot, and the leaf records in that order */
 __global__ void unpack_index_kernel(const unsigned long long *keys, int n, const float4 *A, const float4 *B,
-                                    int *prim_index, float4 *leafA, float4 *leafB)
+                                    int *prim_index, float4 *leaves)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	int p = (int) (unsigned int) (keys[i] & 0xffffffffull);
 	prim_index[i] = p;
-	leafA[i] = A[p];
-	leafB[i] = B[p];
+	write_leaf(leaves, i, p, A, B);
 }
 
 /* ---- Karras hierarchy ---------------------------------------------------- */
@@ -206,6 +217,45 @@ __global__ void refit_kernel(const int *children, const int *parent, const float
 	}
 }
 
+/* ---- packed tree ---------------------------------------------------------- */
+
+/* binary32 box coordinate -> binary16 in the tree's frame, rounded outwards.  The frame change is
+ * computed in binary32 first; its rounding (and that of the walk's own o - center) is at most
+ * 2^-23 of the value, which the nudge below and the `extra` pad of the boxes cover. */
+__device__ __forceinline__ unsigned short pack_lo(float v, float c, float s)
+{
+	float t = (v - c) * s;
+	t -= fabsf(t) * 0x1p-20f;
+	return __half_as_ushort(__float2half_rd(t));
+}
+
+__device__ __forceinline__ unsigned short pack_hi(float v, float c, float s)
+{
+	float t = (v - c) * s;
+	t += fabsf(t) * 0x1p-20f;
+	return __half_as_ushort(__float2half_ru(t));
+}
+
+__global__ void pack_nodes_kernel(const float4 *nodes, int num_nodes, float cx, float cy, float cz, float s, uint4 *packed)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= num_nodes) return;
+	const float4 *nd = nodes + 4 * (size_t) i;
+	float4 llo = nd[0], lhi = nd[1], rlo = nd[2], rhi = nd[3];
+	auto two = [](unsigned short a, unsigned short b) { return (unsigned) a | ((unsigned) b << 16); };
+	uint4 q0, q1;
+	q0.x = two(pack_lo(llo.x, cx, s), pack_lo(llo.y, cy, s));
+	q0.y = two(pack_lo(llo.z, cz, s), pack_hi(lhi.x, cx, s));
+	q0.z = two(pack_hi(lhi.y, cy, s), pack_hi(lhi.z, cz, s));
+	q0.w = two(pack_lo(rlo.x, cx, s), pack_lo(rlo.y, cy, s));
+	q1.x = two(pack_lo(rlo.z, cz, s), pack_hi(rhi.x, cx, s));
+	q1.y = two(pack_hi(rhi.y, cy, s), pack_hi(rhi.z, cz, s));
+	q1.z = (unsigned) __float_as_int(llo.w);
+	q1.w = (unsigned) __float_as_int(rlo.w);
+	packed[2 * (size_t) i] = q0;
+	packed[2 * (size_t) i + 1] = q1;
+}
+
 /* ---- host side ------------------------------------------------------------ */
 
 struct Scratch {
@@ -217,19 +267,19 @@ static int *g_children_of(RtLbvh *bvh) { return bvh->parent + (2 * (size_t) bvh-
 
 void rt_lbvh_free(RtLbvh *bvh)
 {
-	cudaFree(bvh->nodes); cudaFree(bvh->prim_index); cudaFree(bvh->parent);
+	cudaFree(bvh->nodes); cudaFree(bvh->packed); cudaFree(bvh->prim_index); cudaFree(bvh->parent);
 	cudaFree(bvh->leaf_lo); cudaFree(bvh->leaf_hi); cudaFree(bvh->visit);
-	cudaFree(bvh->leafA); cudaFree(bvh->leafB);
+	cudaFree(bvh->leaves);
 	*bvh = RtLbvh();
 }
 
 RtBvhView rt_lbvh_view(const RtLbvh *bvh)
 {
 	RtBvhView v;
-	v.nodes = bvh->nodes;
-	v.prim_index = bvh->prim_index;
-	v.leafA = bvh->leafA;
-	v.leafB = bvh->leafB;
+	v.nodes = bvh->packed;
+	v.cx = bvh->cx; v.cy = bvh->cy; v.cz = bvh->cz;
+	v.scale = bvh->scale; v.inv_scale = bvh->inv_scale;
+	v.leaves = bvh->leaves;
 	v.num_prims = bvh->num_prims;
 	v.depth = bvh->depth;
 	v.t_slack = bvh->t_slack;
@@ -263,6 +313,23 @@ int rt_lbvh_refit(RtLbvh *bvh, const float4 *geomA, const float4 *geomB, float d
 		refit_kernel<<<blocks, 256, 0, stream>>>(g_children_of(bvh), bvh->parent, bvh->leaf_lo, bvh->leaf_hi, n,
 		                                         bvh->visit, (float4 *) node_box.p, bvh->nodes);
 		LCU(cudaGetLastError());
+		/* the frame of the packed boxes: centred on the (padded) bounds, scaled by a power of two so
+		 * that they span about +-2^14 (binary16 overflows at 65504; an overflowing face becomes
+		 * infinite, which is still conservative) */
+		double pad = (double) sqrt(pads.fuzz_r2) + pads.extra + pads.cube_pad;
+		double hx = 0.5 * ((double) bvh->hi.x - bvh->lo.x) + pad, hy = 0.5 * ((double) bvh->hi.y - bvh->lo.y) + pad,
+		       hz = 0.5 * ((double) bvh->hi.z - bvh->lo.z) + pad;
+		double half = fmax(fmax(hx, hy), fmax(hz, 1e-30));
+		int e = (int) floor(log2(16384.0 / half));
+		if (e > 100) e = 100;
+		if (e < -100) e = -100;
+		bvh->scale = (float) ldexp(1.0, e);
+		bvh->inv_scale = (float) ldexp(1.0, -e);
+		bvh->cx = (float) (0.5 * ((double) bvh->hi.x + bvh->lo.x));
+		bvh->cy = (float) (0.5 * ((double) bvh->hi.y + bvh->lo.y));
+		bvh->cz = (float) (0.5 * ((double) bvh->hi.z + bvh->lo.z));
+		pack_nodes_kernel<<<(n - 1 + 255) / 256, 256, 0, stream>>>(bvh->nodes, n - 1, bvh->cx, bvh->cy, bvh->cz, bvh->scale, bvh->packed);
+		LCU(cudaGetLastError());
 		LCU(cudaStreamSynchronize(stream));
 	}
 	bvh->d_max = d_max;
@@ -270,13 +337,11 @@ int rt_lbvh_refit(RtLbvh *bvh, const float4 *geomA, const float4 *geomB, float d
 	return RT_OK;
 }
 
-__global__ void gather_leaves_kernel(const int *prim_index, int n, const float4 *A, const float4 *B, float4 *leafA, float4 *leafB)
+__global__ void gather_leaves_kernel(const int *prim_index, int n, const float4 *A, const float4 *B, float4 *leaves)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
-	int p = prim_index[i];
-	leafA[i] = A[p];
-	leafB[i] = B[p];
+	write_leaf(leaves, i, prim_index[i], A, B);
 }
 
 /* Objects moved (same count): keep the topology, refresh the leaf records and refit
@@ -290,7 +355,7 @@ int rt_lbvh_update(RtLbvh *bvh, const float4 *geomA, const float4 *geomB, const 
 	if (hs->n != n) return lfail(RT_ERR_ARG, "LBVH update: %d objects, the tree was built for %d", hs->n, n);
 	bvh->lo = hs->bounds_lo;
 	bvh->hi = hs->bounds_hi;
-	gather_leaves_kernel<<<(n + 255) / 256, 256, 0, stream>>>(bvh->prim_index, n, geomA, geomB, bvh->leafA, bvh->leafB);
+	gather_leaves_kernel<<<(n + 255) / 256, 256, 0, stream>>>(bvh->prim_index, n, geomA, geomB, bvh->leaves);
 	LCU(cudaGetLastError());
 	float d_max = rt_lbvh_default_dmax((double) hs->bounds_hi.x - hs->bounds_lo.x, (double) hs->bounds_hi.y - hs->bounds_lo.y,
 	                                   (double) hs->bounds_hi.z - hs->bounds_lo.z);
@@ -307,14 +372,15 @@ int rt_lbvh_build(RtLbvh *bvh, const float4 *geomA, const float4 *geomB, int n,
 	bvh->hi = hs->bounds_hi;
 	size_t nn = (size_t) n;
 	LCU(cudaMalloc(&bvh->nodes, sizeof(float4) * 4 * (nn > 1 ? nn - 1 : 1)));
+	LCU(cudaMalloc(&bvh->packed, sizeof(uint4) * 2 * (nn > 1 ? nn - 1 : 1)));
 	LCU(cudaMalloc(&bvh->prim_index, sizeof(int) * nn));
 	/* parent[0 .. 2n-1) followed by children[0 .. 2(n-1)) */
 	LCU(cudaMalloc(&bvh->parent, sizeof(int) * ((2 * nn - 1) + 2 * (nn > 1 ? nn - 1 : 1))));
 	LCU(cudaMalloc(&bvh->leaf_lo, sizeof(float4) * nn));
 	LCU(cudaMalloc(&bvh->leaf_hi, sizeof(float4) * nn));
 	LCU(cudaMalloc(&bvh->visit, sizeof(unsigned int) * (nn > 1 ? nn - 1 : 1)));
-	LCU(cudaMalloc(&bvh->leafA, sizeof(float4) * nn));
-	LCU(cudaMalloc(&bvh->leafB, sizeof(float4) * nn));
+	if (nn >= (1u << 30)) return lfail(RT_ERR_ARG, "the LBVH holds at most 2^30 primitives");
+	LCU(cudaMalloc(&bvh->leaves, sizeof(float4) * 2 * nn));
 
 	Scratch keys_in, keys_out, temp;
 	LCU(cudaMalloc(&keys_in.p, sizeof(unsigned long long) * nn));
@@ -335,7 +401,7 @@ int rt_lbvh_build(RtLbvh *bvh, const float4 *geomA, const float4 *geomB, int n,
 	LCU(cub::DeviceRadixSort::SortKeys(temp.p, temp_bytes, (const unsigned long long *) keys_in.p,
 	                                   (unsigned long long *) keys_out.p, n, 0, 64, stream));
 	unpack_index_kernel<<<blocks, 256, 0, stream>>>((const unsigned long long *) keys_out.p, n, geomA, geomB,
-	                                                bvh->prim_index, bvh->leafA, bvh->leafB);
+	                                                bvh->prim_index, bvh->leaves);
 	LCU(cudaGetLastError());
 	if (n >= 2) {
 		hierarchy_kernel<<<blocks, 256, 0, stream>>>((const unsigned long long *) keys_out.p, n,

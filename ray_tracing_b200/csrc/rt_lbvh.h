@@ -13,11 +13,13 @@
 #include "rt_params.h"
 
 struct RtLbvh {
-	float4 *nodes = nullptr;        /* 4 float4 per internal node (rt_params.h) */
+	float4 *nodes = nullptr;        /* binary32 working copy: 4 float4 per internal node (both child boxes + children) */
+	uint4  *packed = nullptr;       /* what the walk reads: 2 uint4 per internal node, binary16 boxes (rt_params.h) */
+	float   cx = 0, cy = 0, cz = 0, scale = 1, inv_scale = 1;   /* frame of the packed boxes */
 	int    *prim_index = nullptr;   /* Morton order -> primitive index */
 	int    *parent = nullptr;       /* internal-node parents; leaves at [n-1, 2n-1) */
 	float4 *leaf_lo = nullptr, *leaf_hi = nullptr;   /* padded primitive boxes, Morton order */
-	float4 *leafA = nullptr, *leafB = nullptr;       /* geomA / geomB records, Morton order (one load chain fewer per leaf) */
+	float4 *leaves = nullptr;       /* 2 float4 per leaf slot, Morton order: what walk_leaf_screen() loads with one 32-byte load */
 	unsigned int *visit = nullptr;
 	int     num_prims = 0;
 	int     depth = 0;              /* deepest leaf, in levels below the root */

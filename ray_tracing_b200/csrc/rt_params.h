@@ -37,21 +37,27 @@ struct RtSkyView {
 };
 
 /*
- * LBVH (Karras 2012) over primitive AABBs:
- *   nodes[4*i + 0] = left  child box lo.xyz, .w = left child  (int bits)
- *   nodes[4*i + 1] = left  child box hi.xyz
- *   nodes[4*i + 2] = right child box lo.xyz, .w = right child (int bits)
- *   nodes[4*i + 3] = right child box hi.xyz
- * child >= 0: internal node index; child < 0: leaf, ~child = slot in the
- * Morton-sorted order, prim_index[slot] = original primitive index.
+ * LBVH (Karras 2012) over primitive AABBs.  What the walk reads is the PACKED tree: 32 bytes per
+ * internal node, fetched with one 256-bit load (the lanes of a warp sit on different nodes, so the
+ * L1 spends one wavefront per lane and load instruction whatever the width: that pipe was the
+ * limiter of the walk):
+ *   words 0-2   left  child box  lo.x lo.y | lo.z hi.x | hi.y hi.z      binary16, in the tree's own
+ *   words 3-5   right child box  (same)                                  frame x' = (x - center) * scale
+ *   word  6, 7  left, right child
+ * lo is rounded down and hi up, so a packed box contains the binary32 box it came from (which is
+ * itself padded, rt_lbvh_rule.h); scale is a power of two (the frame change is exact up to the
+ * rounding of x - center, covered by the `extra` pad) chosen so that the bounds map to +-2^14.
+ * child >= 0: internal node index; child < 0: leaf, ~child = slot in the Morton-sorted order.
+ * rt_lbvh.cu keeps the binary32 boxes (4 float4 per node) as the refit's working copy.
  */
 struct RtBvhView {
-	const float4 *nodes;
-	const int    *prim_index;
-	const float4 *leafA, *leafB;  /* geomA / geomB in Morton order (leaf slot -> record) */
+	const uint4  *nodes;      /* 2 uint4 per internal node */
+	const float4 *leaves;     /* 2 float4 per leaf slot (Morton order): geomA; geomB.xyz, prim index | type << 30 */
 	int           num_prims;
 	int           depth;      /* deepest leaf (levels below the root) = most stack entries a walk can hold */
-	float         t_slack;    /* see rt_lbvh.cu: cull only if t_entry > best + slack */
+	float         t_slack;    /* see rt_lbvh_rule.h: cull only if t_entry > best + slack */
+	float         cx, cy, cz; /* the packed boxes' frame */
+	float         scale, inv_scale;
 };
 
 struct RtRenderParams {

@@ -273,7 +273,7 @@ __device__ __forceinline__ unsigned warp_step(Path &p, Walk &w, Stack &st, const
 		}
 		const bool walking = p.mode == MODE_WALK;
 		const f3 ro = p.ray_o, dn = p.ray_d;
-		if (walking) walk_nodes(P.bvh, ro, walk_inverse(dn), w, st, RT_WALK_ITERS);
+		if (walking) walk_nodes(P.bvh, walk_ray(P.bvh, ro, dn), w, st, RT_WALK_ITERS);
 		__syncwarp();
 		int prim = 0;
 		float nb = 0.0f, discr = 0.0f;

@@ -35,6 +35,26 @@
 
 typedef struct { float x, y, z, w; } f4;
 
+/* ---- binary16 with directed rounding (rt_lbvh.cu: pack_lo / pack_hi) ---- */
+static float h2f(uint16_t b) { _Float16 h; memcpy(&h, &b, 2); return (float) h; }
+static uint16_t f2h(float f) { _Float16 h = (_Float16) f; uint16_t b; memcpy(&b, &h, 2); return b; }
+
+static float half_dir(float t, int up)
+{
+	uint16_t b = f2h(t);                 /* round to nearest, then step if that went the wrong way */
+	float r = h2f(b);
+	if (up ? r < t : r > t) {
+		if (up) b = (b & 0x8000) ? (b == 0x8000 ? 0x0001 : b - 1) : b + 1;
+		else    b = (b & 0x8000) ? b + 1 : (b == 0x0000 ? 0x8001 : b - 1);
+		r = h2f(b);
+	}
+	return r;
+}
+
+static float pack_lo(float v, float c, float s) { float t = (v - c) * s; t -= fabsf(t) * 0x1p-20f; return half_dir(t, 0); }
+static float pack_hi(float v, float c, float s) { float t = (v - c) * s; t += fabsf(t) * 0x1p-20f; return half_dir(t, 1); }
+
+
 /* ---- the rejected per-node rule (experiment only) ---- */
 #define DYN_KE       (32.0f * 0x1p-24f)         /* K eps = 2^-19 */
 #define DYN_SQRT_KE  0x1.6a09e8p-10f            /* sqrt(K eps), rounded up */
@@ -66,6 +86,8 @@ typedef struct {
 	float *leaf_w;
 	float emag;
 	int depth;          /* deepest leaf, levels below the root */
+	int packed;         /* SIM_PACK: boxes rounded outwards to binary16 in the frame below (rt_params.h) */
+	float cx, cy, cz, scale, inv_scale;
 	int global_pad;     /* the product's static rule */
 	float t_slack;
 } Tree;
@@ -239,6 +261,27 @@ static void build(Tree *T, const RtoObject *obj, int n, int global_pad)
 		}
 		free(blo); free(bhi); free(bw); free(visit);
 	}
+	if (getenv("SIM_PACK") && global_pad && n >= 2) {
+		/* rt_lbvh.cu: rt_lbvh_refit(): the frame, then every box rounded outwards to binary16 */
+		double pad = sqrt(fuzz_r2) + extra + cube_pad;
+		double hx = 0.5 * ((double) hi[0] - lo[0]) + pad, hy = 0.5 * ((double) hi[1] - lo[1]) + pad, hz = 0.5 * ((double) hi[2] - lo[2]) + pad;
+		double half = fmax(fmax(hx, hy), fmax(hz, 1e-30));
+		int e = (int) floor(log2(16384.0 / half));
+		if (e > 100) e = 100;
+		if (e < -100) e = -100;
+		T->packed = 1;
+		T->scale = (float) ldexp(1.0, e);
+		T->inv_scale = (float) ldexp(1.0, -e);
+		T->cx = (float) (0.5 * ((double) hi[0] + lo[0]));
+		T->cy = (float) (0.5 * ((double) hi[1] + lo[1]));
+		T->cz = (float) (0.5 * ((double) hi[2] + lo[2]));
+		for (int i = 0; i < n - 1; i++)
+			for (int k = 0; k < 4; k += 2) {
+				f4 *l = &T->nodes[4 * (size_t) i + k], *h = l + 1;
+				l->x = pack_lo(l->x, T->cx, T->scale); l->y = pack_lo(l->y, T->cy, T->scale); l->z = pack_lo(l->z, T->cz, T->scale);
+				h->x = pack_hi(h->x, T->cx, T->scale); h->y = pack_hi(h->y, T->cy, T->scale); h->z = pack_hi(h->z, T->cz, T->scale);
+			}
+	}
 	free(A); free(B); free(keys); free(children); free(parent); free(first); free(count);
 }
 
@@ -289,6 +332,13 @@ static void walk(const Tree *T, const RtoObject *obj, const float ray[6], Best *
 	float inv[3] = {1.0f / d[0], 1.0f / d[1], 1.0f / d[2]};
 	if (g_fma)      /* rt_device.cuh: walk_inverse() keeps the reciprocals finite for the fma form */
 		for (int k = 0; k < 3; k++) inv[k] = copysignf(fminf(fabsf(inv[k]), 0x1p100f), inv[k]);
+	float ow[3] = {o[0], o[1], o[2]};        /* world origin for nothing but clarity: primitives use `ray` */
+	(void) ow;
+	if (T->packed) {
+		/* rt_device.cuh: walk_ray() */
+		inv[0] *= T->inv_scale; inv[1] *= T->inv_scale; inv[2] *= T->inv_scale;
+		o[0] = (o[0] - T->cx) * T->scale; o[1] = (o[1] - T->cy) * T->scale; o[2] = (o[2] - T->cz) * T->scale;
+	}
 	Best best = {FLT_MAX, -1};
 	if (anyhit_light >= 0) {
 		(*tests)++;

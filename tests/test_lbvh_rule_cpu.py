@@ -54,7 +54,7 @@ def _run(sim, scene, w, h, gens, cam=None, env=None, extra=()):
 def test_static_rule_matches_linear_scan(sim):
     scene = _scene(20000, 5, "spheres20k.bin")
     # the device's slab form (fma), with zero / tiny direction components mixed into the secondary rays
-    r = _run(sim, scene, 96, 54, 2, env={"SIM_FMA": "1", "SIM_AXIS": "1"})
+    r = _run(sim, scene, 96, 54, 2, env={"SIM_FMA": "1", "SIM_PACK": "1", "SIM_AXIS": "1"})
     assert r["mismatches"] == 0 and r["rays"] > 12000, r
     assert r["nodes_per_ray"] < 60 and r["deepest_stack"] <= 32, r
 
@@ -62,7 +62,7 @@ def test_static_rule_matches_linear_scan(sim):
 def test_static_rule_far_camera_after_refit(sim):
     scene = _scene(20000, 5, "spheres20k.bin")
     # camera 600 away looking at the cloud: rt_api.cu re-pads for 1.05 x the distance to the farthest corner
-    r = _run(sim, scene, 128, 72, 1, cam=(400, 300, 420, -1, -0.72, -1), env={"SIM_FMA": "1", "SIM_DMAX": "760"})
+    r = _run(sim, scene, 128, 72, 1, cam=(400, 300, 420, -1, -0.72, -1), env={"SIM_FMA": "1", "SIM_PACK": "1", "SIM_DMAX": "760"})
     assert r["mismatches"] == 0, r
 
 
@@ -72,8 +72,32 @@ def test_mixed_cubes_and_spheres(sim):
     objs = random_scene(3000, seed=3, extent=30.0)
     path = os.path.join(SIM_DIR, "mixed3000.bin")
     np.ascontiguousarray(objs).tofile(path)
-    r = _run(sim, path, 120, 68, 2, cam=(40, 25, 40, -1, -0.6, -1), env={"SIM_FMA": "1", "SIM_AXIS": "1"})
+    r = _run(sim, path, 120, 68, 2, cam=(40, 25, 40, -1, -0.6, -1), env={"SIM_FMA": "1", "SIM_PACK": "1", "SIM_AXIS": "1"})
     assert r["mismatches"] == 0 and r["rays"] > 8000, r
+
+
+def test_axis_parallel_and_degenerate_directions(sim):
+    """The rays of tests/test_gpu_parity.py::test_trace_random_scenes_linear_and_lbvh: one-hot
+    directions, zero components, 1e-7-long directions.  (With an infinite reciprocal the fma slab
+    form turned inf - inf into a NaN that emptied an unbounded interval: walk_inverse() caps it.)"""
+    from conftest import random_scene
+
+    for seed, n, spheres in ((1, 200, True), (2, 1024, False)):
+        objs = random_scene(n, seed, spheres_only=spheres)
+        path = os.path.join(SIM_DIR, f"rand{n}.bin")
+        np.ascontiguousarray(objs).tofile(path)
+        rng = np.random.default_rng(seed + 100)
+        m = 20000
+        rays = np.concatenate([rng.uniform(-8, 8, (m, 3)), rng.normal(size=(m, 3))], axis=1).astype(np.float32)
+        tgt = objs["geom"][rng.integers(0, n, m // 2), :3] + rng.normal(scale=0.3, size=(m // 2, 3))
+        rays[m // 2:, 3:] = tgt - rays[m // 2:, :3]
+        rays[:50, 3:] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, 50)] * rng.choice([-1, 1], (50, 1))
+        rays[50:60, 3:] = 1e-7
+        rays[60:70, 4] = 0.0
+        rpath = os.path.join(SIM_DIR, f"rays{n}.bin")
+        rays.tofile(rpath)
+        r = _run(sim, path, 200, 100, 0, env={"SIM_FMA": "1", "SIM_PACK": "1", "SIM_RAYS": rpath})
+        assert r["mismatches"] == 0 and r["rays"] == m, r
 
 
 def test_rejected_per_node_rule_is_sound_too(sim):
