@@ -1029,9 +1029,10 @@ static int render_pass(const RtCamera *cam, void *fb, int w, int h, const RtRend
 	int rc = pick_traversal(o->traversal, &pl.lbvh);
 	if (rc != RT_OK) return rc;
 	pl.exact = o->variant == RT_VARIANT_EXACT;
-	/* AUTO: the queued kernel (4K scene_0: 1.91 ms against 2.20 ms persistent; 100k spheres
-	 * 4K: 53.9 ms against 55.3 ms) */
-	pl.queued = (o->kernel == RT_KERNEL_QUEUED || o->kernel == RT_KERNEL_AUTO) && o->scale <= 64;   /* tile width is packed into 7 bits */
+	/* AUTO: the queued kernel for linear-scan scenes (4K scene_0: 1.88 ms against 2.20 ms persistent),
+	 * the persistent kernel over the LBVH (100k spheres 4K: 39.3 ms against 44.5 ms: its smaller shared
+	 * memory footprint lets 8 CTAs per SM hide the node-fetch latency) */
+	pl.queued = (o->kernel == RT_KERNEL_QUEUED || (o->kernel == RT_KERNEL_AUTO && !pl.lbvh)) && o->scale <= 64;   /* tile width is packed into 7 bits */
 	pl.persistent = o->kernel == RT_KERNEL_PERSISTENT || o->kernel == RT_KERNEL_AUTO || pl.queued;
 	pl.wavefront = o->kernel == RT_KERNEL_WAVEFRONT;
 	/* a tree deeper than the shared-memory traversal stacks is walked by the local-stack build

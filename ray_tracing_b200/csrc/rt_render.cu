@@ -333,8 +333,15 @@ render_pixel_kernel(const __grid_constant__ RtRenderParams P)
 #define RT_PERSISTENT_MIN_BLOCKS 6   /* 80 registers, 24 warps/SM: best of 5/6/8 on 4K scene_0 (2.39 / 2.37 / 2.51 ms) */
 #endif
 
+/* LBVH kernels.  Once the node fetch was down to one 32-byte load the walk became latency bound
+ * and resident warps started to pay: BASELINE config 5 at 4K, persistent kernel, 5 / 6 / 7 / 8 / 9 /
+ * 10 CTAs per SM (96 / 80 / 72 / 64 / 56 / 48 registers): 47.3 / 42.3 / 39.8 / 39.3 / 40.1 / 40.7 ms.
+ * The queued kernel's extra shared memory (finish / refill queues) caps it at 5-6 CTAs: 44.5 ms. */
 #ifndef RT_LBVH_MIN_BLOCKS
-#define RT_LBVH_MIN_BLOCKS 5         /* LBVH kernels: path + walk state live across warp steps */
+#define RT_LBVH_MIN_BLOCKS 8
+#endif
+#ifndef RT_LBVH_QUEUED_MIN_BLOCKS
+#define RT_LBVH_QUEUED_MIN_BLOCKS 5
 #endif
 
 /* TRAV: 0 = linear scan from shared memory, 1 = LBVH with the traversal stacks in
@@ -492,7 +499,7 @@ __device__ __forceinline__ void rq_drain(const RtRenderParams &P, const SharedSc
 #endif
 
 template <bool LBVH>
-__global__ void __launch_bounds__(RT_BLOCK_THREADS, LBVH ? RT_LBVH_MIN_BLOCKS : RT_QUEUED_MIN_BLOCKS)
+__global__ void __launch_bounds__(RT_BLOCK_THREADS, LBVH ? RT_LBVH_QUEUED_MIN_BLOCKS : RT_QUEUED_MIN_BLOCKS)
 render_queued_kernel(const __grid_constant__ RtRenderParams P)
 {
 	extern __shared__ __align__(16) unsigned char smem[];
