@@ -50,6 +50,11 @@ typedef struct {
 	RtVector3 bounds_lo, bounds_hi;
 	int       num_spheres, num_cubes;
 	int       div_safe;      /* every cube coordinate is zero or has magnitude in [2^-37, 2^59] */
+	/* the ONE object whose emission_color*emission_power is not (+-0, +-0, +-0), or -1 when there
+	 * are none or several.  A light sample only asks what its nearest hit EMITS (main.c:199-204:
+	 * sampled += emission_color * emission_power of hit2.object), and adding a zero vector changes
+	 * nothing, so with a single emitter the question is "is the emitter the nearest hit?" */
+	int       only_emitter;
 } RtPackedScene;
 
 int  rt_host_pack_scene(const RtObject *objects, int n, RtPackedScene *out);

@@ -43,6 +43,9 @@ static int lfail(int code, const char *fmt, ...)
 static double g_fuzz_k = RT_LBVH_FUZZ_K;
 static double g_slack = RT_LBVH_SLACK;
 extern "C" void rt_lbvh_debug_set(double k, double slack) { g_fuzz_k = k; g_slack = slack; }
+/* test / A-B knob: 0 = light samples walk to their nearest hit like every other ray */
+static int g_anyhit = 1;
+extern "C" void rt_lbvh_debug_set_anyhit(int on) { g_anyhit = on ? 1 : 0; }
 
 /* ---- Morton keys -------------------------------------------------------- */
 
@@ -283,6 +286,9 @@ RtBvhView rt_lbvh_view(const RtLbvh *bvh)
 	v.num_prims = bvh->num_prims;
 	v.depth = bvh->depth;
 	v.t_slack = bvh->t_slack;
+	v.emitter_prim = g_anyhit ? bvh->emitter_prim : -1;
+	v.emitter_slot = g_anyhit ? bvh->emitter_slot : -1;
+	if (v.emitter_slot < 0) v.emitter_prim = -1;
 	return v;
 }
 
@@ -337,6 +343,30 @@ int rt_lbvh_refit(RtLbvh *bvh, const float4 *geomA, const float4 *geomB, float d
 	return RT_OK;
 }
 
+/* Morton slot of primitive `prim` (the scene's only emitter) */
+__global__ void find_slot_kernel(const int *prim_index, int n, int prim, int *slot_out)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n && prim_index[i] == prim) *slot_out = i;
+}
+
+static int locate_emitter(RtLbvh *bvh, int prim, cudaStream_t stream)
+{
+	bvh->emitter_prim = -1;
+	bvh->emitter_slot = -1;
+	int n = bvh->num_prims;
+	if (prim < 0 || prim >= n) return RT_OK;
+	/* visit[0] is free between refits (it doubles as a result cell, as for the depth) */
+	int slot = -1;
+	LCU(cudaMemcpyAsync(bvh->visit, &slot, sizeof(int), cudaMemcpyHostToDevice, stream));
+	find_slot_kernel<<<(n + 255) / 256, 256, 0, stream>>>(bvh->prim_index, n, prim, (int *) bvh->visit);
+	LCU(cudaGetLastError());
+	LCU(cudaMemcpyAsync(&slot, bvh->visit, sizeof(int), cudaMemcpyDeviceToHost, stream));
+	LCU(cudaStreamSynchronize(stream));
+	if (slot >= 0) { bvh->emitter_prim = prim; bvh->emitter_slot = slot; }
+	return RT_OK;
+}
+
 __global__ void gather_leaves_kernel(const int *prim_index, int n, const float4 *A, const float4 *B, float4 *leaves)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -357,6 +387,8 @@ int rt_lbvh_update(RtLbvh *bvh, const float4 *geomA, const float4 *geomB, const 
 	bvh->hi = hs->bounds_hi;
 	gather_leaves_kernel<<<(n + 255) / 256, 256, 0, stream>>>(bvh->prim_index, n, geomA, geomB, bvh->leaves);
 	LCU(cudaGetLastError());
+	int rc = locate_emitter(bvh, hs->only_emitter, stream);
+	if (rc != RT_OK) return rc;
 	float d_max = rt_lbvh_default_dmax((double) hs->bounds_hi.x - hs->bounds_lo.x, (double) hs->bounds_hi.y - hs->bounds_lo.y,
 	                                   (double) hs->bounds_hi.z - hs->bounds_lo.z);
 	return rt_lbvh_refit(bvh, geomA, geomB, d_max, stream);
@@ -416,6 +448,8 @@ int rt_lbvh_build(RtLbvh *bvh, const float4 *geomA, const float4 *geomB, int n,
 		LCU(cudaMemcpyAsync(&bvh->depth, bvh->visit, sizeof(int), cudaMemcpyDeviceToHost, stream));
 	}
 	LCU(cudaStreamSynchronize(stream));
+	int rc = locate_emitter(bvh, hs->only_emitter, stream);
+	if (rc != RT_OK) return rc;
 
 	/* secondary rays start on surfaces, i.e. inside the primitive bounds: their
 	 * distance to any primitive is at most the bounds' diagonal.  The renderer

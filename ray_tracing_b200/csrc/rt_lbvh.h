@@ -23,6 +23,8 @@ struct RtLbvh {
 	unsigned int *visit = nullptr;
 	int     num_prims = 0;
 	int     depth = 0;              /* deepest leaf, in levels below the root */
+	int     emitter_prim = -1;      /* RtPackedScene::only_emitter and its Morton slot (-1: none or several) */
+	int     emitter_slot = -1;
 	float   d_max = 0.0f;           /* largest origin-to-primitive distance the padding covers */
 	float   t_slack = 0.0f;
 	RtVector3 lo = {0, 0, 0}, hi = {0, 0, 0};   /* unpadded bounds of all primitives */

@@ -58,6 +58,9 @@ struct RtBvhView {
 	float         t_slack;    /* see rt_lbvh_rule.h: cull only if t_entry > best + slack */
 	float         cx, cy, cz; /* the packed boxes' frame */
 	float         scale, inv_scale;
+	/* light samples in any-hit mode (rt_render.cu: warp_step): the scene's only emitting primitive
+	 * and its leaf slot, or -1, -1 */
+	int           emitter_prim, emitter_slot;
 };
 
 struct RtRenderParams {

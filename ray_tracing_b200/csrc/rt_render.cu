@@ -265,9 +265,16 @@ __device__ __forceinline__ unsigned warp_step(Path &p, Walk &w, Stack &st, const
 		}
 	} else {
 		const unsigned full = 0xffffffffu;
+		/* Light samples in any-hit mode.  A sample adds what its nearest hit EMITS (main.c:199-204),
+		 * so when one primitive is the scene's only emitter (bvh.emitter_prim) the walk only has
+		 * to decide whether that primitive is the nearest hit: its leaf is tested first (parked
+		 * here), its distance bounds the walk, and the first primitive accepted in front of it
+		 * (or tying with a lower index) ends the walk -- as does missing the emitter. */
+		const bool anyhit = p.shadow && P.bvh.emitter_slot >= 0;
 		if (p.mode == MODE_TRACE) {
 			p.ray_d = unit3(p.ray_d);           /* scene.c:158; kept for the steps the walk lasts */
 			walk_begin(w, P.bvh);
+			if (anyhit) w.leaf = ~P.bvh.emitter_slot;
 			p.mode = MODE_WALK;
 			traced = 1;
 		}
@@ -278,10 +285,12 @@ __device__ __forceinline__ unsigned warp_step(Path &p, Walk &w, Stack &st, const
 		int prim = 0;
 		float nb = 0.0f, discr = 0.0f;
 		bool roots = false;
-		if (walking && w.leaf) roots = walk_leaf_screen(P.bvh, ro, dn, w, prim, nb, discr);
+		const bool leafed = walking && w.leaf;
+		if (leafed) roots = walk_leaf_screen(P.bvh, ro, dn, w, prim, nb, discr);
 		__syncwarp();
 		if (roots) walk_leaf_root(dn, prim, nb, discr, w);
 		__syncwarp();
+		if (leafed && anyhit && w.best.obj != P.bvh.emitter_prim) { w.node = RT_WALK_DONE; w.sp = 0; }
 		if (walking && walk_over(w)) p.mode = MODE_HIT;
 		const unsigned hits = __ballot_sync(full, p.mode == MODE_HIT);
 		if (hits == 0) return traced;

@@ -60,6 +60,8 @@ int rt_host_pack_scene(const RtObject *objects, int n, RtPackedScene *out)
 	out->n = n;
 	out->light_index = -1;
 	out->div_safe = 1;
+	out->only_emitter = -1;
+	int emitters = 0;
 	size_t cnt = n > 0 ? (size_t) n : 1;
 	out->geomA = (RtF4 *) calloc(cnt, sizeof(RtF4));
 	out->geomB = (RtF4 *) calloc(cnt, sizeof(RtF4));
@@ -129,11 +131,16 @@ int rt_host_pack_scene(const RtObject *objects, int n, RtPackedScene *out)
 		M[2].y = m->emission_color.y * m->emission_power;
 		M[2].z = m->emission_color.z * m->emission_power;
 		M[2].w = m->emission_power;
+		if (!(M[2].x == 0 && M[2].y == 0 && M[2].z == 0)) {    /* NaN counts as emitting */
+			emitters++;
+			out->only_emitter = i;
+		}
 		M[3].x = m->albedo.x * om;                             /* main.c:248 */
 		M[3].y = m->albedo.y * om;
 		M[3].z = m->albedo.z * om;
 		M[3].w = 0;
 	}
+	if (emitters != 1) out->only_emitter = -1;
 	return RT_OK;
 }
 

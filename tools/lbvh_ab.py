@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--sizes", default="1920x1080,3840x2160")
     ap.add_argument("--one", action="store_true", help="render the first size with the first kernel three times and exit (for ncu)")
     ap.add_argument("--counts", default=None, help="counter build (-DRT_COUNT_WALK): write nodes / tests per ray of the last size to this JSON file")
+    ap.add_argument("--no-anyhit", action="store_true", help="light samples walk to their nearest hit (rt_lbvh_debug_set_anyhit(0))")
     a = ap.parse_args()
     import torch
 
@@ -37,6 +38,8 @@ def main():
     K = {"pixel": host.RT_KERNEL_PIXEL, "persistent": host.RT_KERNEL_PERSISTENT, "wavefront": host.RT_KERNEL_WAVEFRONT,
          "queued": host.RT_KERNEL_QUEUED, "auto": host.RT_KERNEL_AUTO}
     r = host.Renderer(num_gpus=1)
+    if a.no_anyhit:
+        host.load_library().rt_lbvh_debug_set_anyhit(0)
     r.upload_skybox(scenes.procedural_skybox(256, seed=11))
     r.upload_scene(host.parse_scene_string_large(scenes.synthetic_spheres_text(a.n)))
     cam = host.Camera()
