@@ -11,7 +11,6 @@
  * checked on the CPU against the O(N) scan by tests/lbvh_sim.c.
  */
 #include <cub/device/device_radix_sort.cuh>
-#include <cuda_fp16.h>
 
 #include <math.h>
 #include <stdarg.h>
@@ -222,21 +221,23 @@ __global__ void refit_kernel(const int *children, const int *parent, const float
 
 /* ---- packed tree ---------------------------------------------------------- */
 
-/* binary32 box coordinate -> binary16 in the tree's frame, rounded outwards.  The frame change is
- * computed in binary32 first; its rounding (and that of the walk's own o - center) is at most
- * 2^-23 of the value, which the nudge below and the `extra` pad of the boxes cover. */
-__device__ __forceinline__ unsigned short pack_lo(float v, float c, float s)
+/* binary32 box coordinate -> 16-bit fixed point in the tree's frame q = (x - center) * scale + 32768,
+ * rounded outwards and then moved ONE more quantum outwards: the walk evaluates a slab distance as
+ * fma(2^23 + q, inv, -(2^23 + 32768 + o') * inv) (rt_device.cuh: walk_ray, walk_nodes), whose second
+ * term is rounded at the magnitude 2^23 |inv|, i.e. it places the plane up to ~0.51 quanta off.
+ * The frame change is computed in binary32 first; its rounding (at most 2^-9 quanta here, and that of
+ * the walk's own o - center) is covered by the `extra` pad of the boxes.  The frame (rt_lbvh_refit)
+ * leaves 700 quanta of margin at both ends, so the clamps never bind for a box inside the bounds. */
+__device__ __forceinline__ unsigned pack_lo(float v, float c, float s)
 {
-	float t = (v - c) * s;
-	t -= fabsf(t) * 0x1p-20f;
-	return __half_as_ushort(__float2half_rd(t));
+	float t = floorf((v - c) * s) - 1.0f + 32768.0f;
+	return (unsigned) fminf(fmaxf(t, 0.0f), 65535.0f);
 }
 
-__device__ __forceinline__ unsigned short pack_hi(float v, float c, float s)
+__device__ __forceinline__ unsigned pack_hi(float v, float c, float s)
 {
-	float t = (v - c) * s;
-	t += fabsf(t) * 0x1p-20f;
-	return __half_as_ushort(__float2half_ru(t));
+	float t = ceilf((v - c) * s) + 1.0f + 32768.0f;
+	return (unsigned) fminf(fmaxf(t, 0.0f), 65535.0f);
 }
 
 __global__ void pack_nodes_kernel(const float4 *nodes, int num_nodes, float cx, float cy, float cz, float s, uint4 *packed)
@@ -245,14 +246,19 @@ __global__ void pack_nodes_kernel(const float4 *nodes, int num_nodes, float cx, 
 	if (i >= num_nodes) return;
 	const float4 *nd = nodes + 4 * (size_t) i;
 	float4 llo = nd[0], lhi = nd[1], rlo = nd[2], rhi = nd[3];
-	auto two = [](unsigned short a, unsigned short b) { return (unsigned) a | ((unsigned) b << 16); };
+	/* one word per axis: lo | hi << 16.  An empty box (lo > hi: a primitive of unknown type)
+	 * stays empty: 65535 | 0 << 16 on every axis. */
+	auto axis = [](float lo, float hi, float c, float sc) {
+		if (lo > hi) return 65535u;
+		return pack_lo(lo, c, sc) | (pack_hi(hi, c, sc) << 16);
+	};
 	uint4 q0, q1;
-	q0.x = two(pack_lo(llo.x, cx, s), pack_lo(llo.y, cy, s));
-	q0.y = two(pack_lo(llo.z, cz, s), pack_hi(lhi.x, cx, s));
-	q0.z = two(pack_hi(lhi.y, cy, s), pack_hi(lhi.z, cz, s));
-	q0.w = two(pack_lo(rlo.x, cx, s), pack_lo(rlo.y, cy, s));
-	q1.x = two(pack_lo(rlo.z, cz, s), pack_hi(rhi.x, cx, s));
-	q1.y = two(pack_hi(rhi.y, cy, s), pack_hi(rhi.z, cz, s));
+	q0.x = axis(llo.x, lhi.x, cx, s);
+	q0.y = axis(llo.y, lhi.y, cy, s);
+	q0.z = axis(llo.z, lhi.z, cz, s);
+	q0.w = axis(rlo.x, rhi.x, cx, s);
+	q1.x = axis(rlo.y, rhi.y, cy, s);
+	q1.y = axis(rlo.z, rhi.z, cz, s);
 	q1.z = (unsigned) __float_as_int(llo.w);
 	q1.w = (unsigned) __float_as_int(rlo.w);
 	packed[2 * (size_t) i] = q0;
@@ -320,13 +326,12 @@ int rt_lbvh_refit(RtLbvh *bvh, const float4 *geomA, const float4 *geomB, float d
 		                                         bvh->visit, (float4 *) node_box.p, bvh->nodes);
 		LCU(cudaGetLastError());
 		/* the frame of the packed boxes: centred on the (padded) bounds, scaled by a power of two so
-		 * that they span about +-2^14 (binary16 overflows at 65504; an overflowing face becomes
-		 * infinite, which is still conservative) */
+		 * that they span at most +-32000 of the +-32768 quanta (config 5: 1/512 of a unit per quantum) */
 		double pad = (double) sqrt(pads.fuzz_r2) + pads.extra + pads.cube_pad;
 		double hx = 0.5 * ((double) bvh->hi.x - bvh->lo.x) + pad, hy = 0.5 * ((double) bvh->hi.y - bvh->lo.y) + pad,
 		       hz = 0.5 * ((double) bvh->hi.z - bvh->lo.z) + pad;
 		double half = fmax(fmax(hx, hy), fmax(hz, 1e-30));
-		int e = (int) floor(log2(16384.0 / half));
+		int e = (int) floor(log2(32000.0 / half));
 		if (e > 100) e = 100;
 		if (e < -100) e = -100;
 		bvh->scale = (float) ldexp(1.0, e);

@@ -14,7 +14,7 @@
 
 struct RtLbvh {
 	float4 *nodes = nullptr;        /* binary32 working copy: 4 float4 per internal node (both child boxes + children) */
-	uint4  *packed = nullptr;       /* what the walk reads: 2 uint4 per internal node, binary16 boxes (rt_params.h) */
+	uint4  *packed = nullptr;       /* what the walk reads: 2 uint4 per internal node, 16-bit fixed-point boxes (rt_params.h) */
 	float   cx = 0, cy = 0, cz = 0, scale = 1, inv_scale = 1;   /* frame of the packed boxes */
 	int    *prim_index = nullptr;   /* Morton order -> primitive index */
 	int    *parent = nullptr;       /* internal-node parents; leaves at [n-1, 2n-1) */

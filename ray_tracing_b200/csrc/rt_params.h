@@ -41,12 +41,16 @@ struct RtSkyView {
  * internal node, fetched with one 256-bit load (the lanes of a warp sit on different nodes, so the
  * L1 spends one wavefront per lane and load instruction whatever the width: that pipe was the
  * limiter of the walk):
- *   words 0-2   left  child box  lo.x lo.y | lo.z hi.x | hi.y hi.z      binary16, in the tree's own
- *   words 3-5   right child box  (same)                                  frame x' = (x - center) * scale
+ *   words 0-2   left  child box  x, y, z: lo | hi << 16     16-bit fixed point in the tree's own frame
+ *   words 3-5   right child box  (same)                      q = (x - center) * scale + 32768
  *   word  6, 7  left, right child
- * lo is rounded down and hi up, so a packed box contains the binary32 box it came from (which is
- * itself padded, rt_lbvh_rule.h); scale is a power of two (the frame change is exact up to the
- * rounding of x - center, covered by the `extra` pad) chosen so that the bounds map to +-2^14.
+ * lo is rounded down and hi up, plus one quantum each (rt_lbvh.cu: pack_lo), so a packed box contains
+ * the binary32 box it came from (which is itself padded, rt_lbvh_rule.h) with room for the rounding
+ * of the walk's slab arithmetic; scale is a power of two chosen so that the bounds map to +-32000.
+ * One PRMT per plane turns a half word into the binary32 number 2^23 + q AND picks the near or
+ * the far plane of its axis by the ray's sign (rt_device.cuh: walk_nodes), so a box costs 6 PRMT,
+ * 6 FFMA and 4 min/max.  (Until round 2 the boxes were binary16: 12 conversions + 12 FFMA + 20
+ * min/max per node, and 8 times coarser at the rim of the scene.)
  * child >= 0: internal node index; child < 0: leaf, ~child = slot in the Morton-sorted order.
  * rt_lbvh.cu keeps the binary32 boxes (4 float4 per node) as the refit's working copy.
  */

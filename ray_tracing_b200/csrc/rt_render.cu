@@ -224,7 +224,7 @@ __device__ __forceinline__ void walk_counters_flush(const RtRenderParams &P, con
 #endif
 }
 
-__device__ __forceinline__ void stack_init(SharedStack &st, const SharedScene &S) { st.col = S.stack; }
+__device__ __forceinline__ void stack_init(SharedStack &st, const SharedScene &S) { st.init(S.stack); }
 __device__ __forceinline__ void stack_init(LocalStack &, const SharedScene &) {}
 
 /*
@@ -273,7 +273,7 @@ __device__ __forceinline__ unsigned warp_step(Path &p, Walk &w, Stack &st, const
 		const bool anyhit = p.shadow && P.bvh.emitter_slot >= 0;
 		if (p.mode == MODE_TRACE) {
 			p.ray_d = unit3(p.ray_d);           /* scene.c:158; kept for the steps the walk lasts */
-			walk_begin(w, P.bvh);
+			walk_begin(w, P.bvh, st);
 			if (anyhit) w.leaf = ~P.bvh.emitter_slot;
 			p.mode = MODE_WALK;
 			traced = 1;
@@ -290,7 +290,7 @@ __device__ __forceinline__ unsigned warp_step(Path &p, Walk &w, Stack &st, const
 		__syncwarp();
 		if (roots) walk_leaf_root(dn, prim, nb, discr, w);
 		__syncwarp();
-		if (leafed && anyhit && w.best.obj != P.bvh.emitter_prim) { w.node = RT_WALK_DONE; w.sp = 0; }
+		if (leafed && anyhit && w.best.obj != P.bvh.emitter_prim) { w.node = RT_WALK_DONE; w.sp = st.bottom(); }
 		if (walking && walk_over(w)) p.mode = MODE_HIT;
 		const unsigned hits = __ballot_sync(full, p.mode == MODE_HIT);
 		if (hits == 0) return traced;
@@ -323,7 +323,7 @@ render_pixel_kernel(const __grid_constant__ RtRenderParams P)
 	p.mode = MODE_IDLE;
 	Walk w;
 	SharedStack st;
-	stack_init(st, S);
+	if (LBVH) stack_init(st, S);        /* writes the stack sentinel into the area linear-scan scenes stage their objects in */
 	Cell c;
 	bool owns = idx < (unsigned) (P.tiles_x * P.tiles_y) * 32u && cell_of(P, idx, cx, cy);
 	if (owns) {
@@ -371,7 +371,7 @@ render_persistent_kernel(const __grid_constant__ RtRenderParams P)
 	p.mode = MODE_IDLE;
 	Walk w;
 	typename std::conditional<TRAV == 2, LocalStack, SharedStack>::type st;
-	stack_init(st, S);
+	if (LBVH) stack_init(st, S);        /* writes the stack sentinel into the area linear-scan scenes stage their objects in */
 	walk_counters_init(w);
 	Cell c;
 	bool owns = false;          /* lane holds a pixel whose path is running or just ended */
@@ -526,7 +526,7 @@ render_queued_kernel(const __grid_constant__ RtRenderParams P)
 	p.obj = 0;
 	Walk w;
 	SharedStack st;
-	stack_init(st, S);
+	if (LBVH) stack_init(st, S);        /* writes the stack sentinel into the area linear-scan scenes stage their objects in */
 	walk_counters_init(w);
 	int cx0 = 0, cy0 = 0, ctw = 0;  /* output tile of the lane's pixel */
 	bool owns = false;              /* lane holds a pixel whose path is running or just ended */
@@ -774,7 +774,7 @@ render_wavefront_kernel(const __grid_constant__ RtRenderParams P)
 	extern __shared__ __align__(16) unsigned char smem[];
 	SharedScene S = stage_scene(P, smem, !LBVH);
 	size_t scene_bytes = RT_SCENE_HEAD_BYTES +
-	                     (LBVH ? sizeof(int) * RT_SMEM_STACK * RT_BLOCK_THREADS
+	                     (LBVH ? sizeof(int) * (RT_SMEM_STACK + 1) * RT_BLOCK_THREADS
 	                           : 2 * sizeof(float4) * (size_t) P.scene.n + sizeof(int2) * (size_t) P.scene.num_runs);
 	scene_bytes = (scene_bytes + 15) & ~(size_t) 15;
 	const unsigned full = 0xffffffffu;
@@ -1046,7 +1046,7 @@ __global__ void probe_div_kernel(uint64_t seed, unsigned per_thread, int lo_exp_
 static size_t smem_bytes(const RtRenderParams &P, bool lbvh)
 {
 	return RT_SCENE_HEAD_BYTES +
-	       (lbvh ? sizeof(int) * RT_SMEM_STACK * RT_BLOCK_THREADS      /* traversal stacks */
+	       (lbvh ? sizeof(int) * (RT_SMEM_STACK + 1) * RT_BLOCK_THREADS      /* traversal stacks */
 	             : 2 * sizeof(float4) * (size_t) P.scene.n + sizeof(int2) * (size_t) P.scene.num_runs);
 }
 

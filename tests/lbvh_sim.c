@@ -35,25 +35,11 @@
 
 typedef struct { float x, y, z, w; } f4;
 
-/* ---- binary16 with directed rounding (rt_lbvh.cu: pack_lo / pack_hi) ---- */
-static float h2f(uint16_t b) { _Float16 h; memcpy(&h, &b, 2); return (float) h; }
-static uint16_t f2h(float f) { _Float16 h = (_Float16) f; uint16_t b; memcpy(&b, &h, 2); return b; }
-
-static float half_dir(float t, int up)
-{
-	uint16_t b = f2h(t);                 /* round to nearest, then step if that went the wrong way */
-	float r = h2f(b);
-	if (up ? r < t : r > t) {
-		if (up) b = (b & 0x8000) ? (b == 0x8000 ? 0x0001 : b - 1) : b + 1;
-		else    b = (b & 0x8000) ? b + 1 : (b == 0x0000 ? 0x8001 : b - 1);
-		r = h2f(b);
-	}
-	return r;
-}
-
-static float pack_lo(float v, float c, float s) { float t = (v - c) * s; t -= fabsf(t) * 0x1p-20f; return half_dir(t, 0); }
-static float pack_hi(float v, float c, float s) { float t = (v - c) * s; t += fabsf(t) * 0x1p-20f; return half_dir(t, 1); }
-
+/* ---- 16-bit fixed point, rounded outwards plus one quantum (rt_lbvh.cu: pack_lo / pack_hi).
+ * The value kept in the tree is the binary32 number Q = 2^23 + q that the walk's PRMT makes. ---- */
+static float clampq(float t) { return fminf(fmaxf(t, 0.0f), 65535.0f); }
+static float pack_lo(float v, float c, float s) { return 8388608.0f + clampq(floorf((v - c) * s) - 1.0f + 32768.0f); }
+static float pack_hi(float v, float c, float s) { return 8388608.0f + clampq(ceilf((v - c) * s) + 1.0f + 32768.0f); }
 
 /* ---- the rejected per-node rule (experiment only) ---- */
 #define DYN_KE       (32.0f * 0x1p-24f)         /* K eps = 2^-19 */
@@ -86,7 +72,7 @@ typedef struct {
 	float *leaf_w;
 	float emag;
 	int depth;          /* deepest leaf, levels below the root */
-	int packed;         /* SIM_PACK: boxes rounded outwards to binary16 in the frame below (rt_params.h) */
+	int packed;         /* SIM_PACK: boxes rounded outwards to 16-bit fixed point in the frame below (rt_params.h) */
 	float cx, cy, cz, scale, inv_scale;
 	int global_pad;     /* the product's static rule */
 	float t_slack;
@@ -262,11 +248,11 @@ static void build(Tree *T, const RtoObject *obj, int n, int global_pad)
 		free(blo); free(bhi); free(bw); free(visit);
 	}
 	if (getenv("SIM_PACK") && global_pad && n >= 2) {
-		/* rt_lbvh.cu: rt_lbvh_refit(): the frame, then every box rounded outwards to binary16 */
+		/* rt_lbvh.cu: rt_lbvh_refit(): the frame, then every box rounded outwards to 16-bit fixed point */
 		double pad = sqrt(fuzz_r2) + extra + cube_pad;
 		double hx = 0.5 * ((double) hi[0] - lo[0]) + pad, hy = 0.5 * ((double) hi[1] - lo[1]) + pad, hz = 0.5 * ((double) hi[2] - lo[2]) + pad;
 		double half = fmax(fmax(hx, hy), fmax(hz, 1e-30));
-		int e = (int) floor(log2(16384.0 / half));
+		int e = (int) floor(log2(32000.0 / half));
 		if (e > 100) e = 100;
 		if (e < -100) e = -100;
 		T->packed = 1;
@@ -290,8 +276,19 @@ typedef struct { float t; int obj; } Best;
 /* rt_device.cuh: node_overlap with widened boxes */
 static int g_fma;       /* SIM_FMA: slab distances as fma(plane, inv, -(o*inv)) */
 
+static int g_packed;    /* the tree holds Q = 2^23 + q; o[] holds oi = fma(K, inv, o' * inv) (rt_device.cuh: walk_ray) */
+
 static int overlap(f4 lo, f4 hi, const float o[3], const float inv[3], float pad, float tmax, float *tn)
 {
+	if (g_packed) {
+		/* rt_device.cuh: node_span(): near / far plane picked by the sign bit of inv */
+		float nx = fmaf(signbit(inv[0]) ? hi.x : lo.x, inv[0], -o[0]), fx = fmaf(signbit(inv[0]) ? lo.x : hi.x, inv[0], -o[0]);
+		float ny = fmaf(signbit(inv[1]) ? hi.y : lo.y, inv[1], -o[1]), fy = fmaf(signbit(inv[1]) ? lo.y : hi.y, inv[1], -o[1]);
+		float nz = fmaf(signbit(inv[2]) ? hi.z : lo.z, inv[2], -o[2]), fz = fmaf(signbit(inv[2]) ? lo.z : hi.z, inv[2], -o[2]);
+		*tn = fmax2(fmax2(nx, ny), fmax2(nz, 0.0f));
+		float tf = fmin2(fmin2(fx, fy), fmin2(fz, tmax));
+		return *tn <= tf;
+	}
 	if (g_fma) {
 		float ox = o[0] * inv[0], oy = o[1] * inv[1], oz = o[2] * inv[2];
 		float tx1 = fmaf(lo.x, inv[0], -ox), tx2 = fmaf(hi.x, inv[0], -ox);
@@ -331,13 +328,15 @@ static void walk(const Tree *T, const RtoObject *obj, const float ray[6], Best *
 	if (!(n <= 0x1.4f8b58p-17f && n >= -0x1.4f8b58p-17f)) { d[0] /= n; d[1] /= n; d[2] /= n; }
 	float inv[3] = {1.0f / d[0], 1.0f / d[1], 1.0f / d[2]};
 	if (g_fma)      /* rt_device.cuh: walk_inverse() keeps the reciprocals finite for the fma form */
-		for (int k = 0; k < 3; k++) inv[k] = copysignf(fminf(fabsf(inv[k]), 0x1p100f), inv[k]);
+		for (int k = 0; k < 3; k++) inv[k] = copysignf(fminf(fabsf(inv[k]) * (T->packed ? T->inv_scale : 1.0f), 0x1p100f), inv[k]);
 	float ow[3] = {o[0], o[1], o[2]};        /* world origin for nothing but clarity: primitives use `ray` */
 	(void) ow;
 	if (T->packed) {
-		/* rt_device.cuh: walk_ray() */
-		inv[0] *= T->inv_scale; inv[1] *= T->inv_scale; inv[2] *= T->inv_scale;
-		o[0] = (o[0] - T->cx) * T->scale; o[1] = (o[1] - T->cy) * T->scale; o[2] = (o[2] - T->cz) * T->scale;
+		/* rt_device.cuh: walk_ray(): o[] becomes oi */
+		const float K = 8421376.0f;
+		o[0] = fmaf(K, inv[0], (o[0] - T->cx) * T->scale * inv[0]);
+		o[1] = fmaf(K, inv[1], (o[1] - T->cy) * T->scale * inv[1]);
+		o[2] = fmaf(K, inv[2], (o[2] - T->cz) * T->scale * inv[2]);
 	}
 	Best best = {FLT_MAX, -1};
 	if (anyhit_light >= 0) {
@@ -432,6 +431,7 @@ int main(int argc, char **argv)
 	int axis_rays = getenv("SIM_AXIS") != NULL;    /* make some secondary rays (nearly) axis-parallel */
 	Tree T;
 	build(&T, obj, n, global_pad);
+	g_packed = T.packed;
 
 	/* light = first emissive object (main.c:140-146) */
 	int light = -1;
