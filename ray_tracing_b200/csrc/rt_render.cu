@@ -31,6 +31,16 @@ namespace RT_NS {
 /* fixed part of a block's scene area: byte LUT, sweep lists, direction caches */
 #define RT_SCENE_HEAD_BYTES (256 * sizeof(float) + RT_BLOCK_THREADS + (RT_BLOCK_THREADS / 32) * RT_DIR_CACHE_BYTES)
 
+/* The walk's loop wants ~12 more registers than the 64 a thread has at 8 CTAs per SM (ray 6, plane
+ * selectors 6, cull limit, node base); without them the compiler re-derives the selectors and the
+ * limit for every visited node (10 of 69 instructions, all on the ALU pipe, which is what bounds
+ * the walk).  What a path only touches between rays -- contrib and result -- therefore waits in
+ * shared memory while the lane walks (persistent kernel over the LBVH only). */
+#define RT_PARK_WORDS 6
+#ifndef RT_PARK_PATH
+#define RT_PARK_PATH 1
+#endif
+
 struct SharedScene {
 	float4 *A;
 	float4 *B;
@@ -39,6 +49,7 @@ struct SharedScene {
 	float  *dirs;             /* per warp: direction cache of warp_sweep_cached() (RT_DIR_ROW floats per lane) */
 	int2   *runs;             /* type runs of the scene (rt_device.cuh: nearest_linear) */
 	int    *stack;            /* LBVH: this thread's traversal-stack column (rt_device.cuh: SharedStack) */
+	volatile float *park;     /* LBVH: this thread's column of RT_PARK_WORDS words behind the stacks (path_park / path_unpark) */
 };
 
 /* `smem` = start of the scene area: kernels that keep per-warp queues in shared
@@ -53,6 +64,7 @@ __device__ __forceinline__ SharedScene stage_scene(const RtRenderParams &P, unsi
 	s.A = reinterpret_cast<float4 *>(smem + RT_SCENE_HEAD_BYTES);
 	s.B = s.A + 1;            /* records interleaved: A[2*i], B[2*i] are neighbours (one address per object) */
 	s.stack = reinterpret_cast<int *>(s.A) + threadIdx.x;   /* LBVH scenes stage no objects: the area holds the stacks */
+	s.park = reinterpret_cast<float *>(s.A) + (RT_SMEM_STACK + 1) * RT_BLOCK_THREADS + threadIdx.x;
 	s.runs = reinterpret_cast<int2 *>(s.A + (linear ? 2 * P.scene.n : 0));
 	for (int i = threadIdx.x; i < 256; i += blockDim.x) s.lut[i] = __ldg(&P.byte_lut[i]);
 	if (linear)
@@ -225,6 +237,24 @@ __device__ __forceinline__ void walk_counters_flush(const RtRenderParams &P, con
 }
 
 __device__ __forceinline__ void stack_init(SharedStack &st, const SharedScene &S) { st.init(S.stack); }
+
+template <bool PARK>
+__device__ __forceinline__ void path_park(const Path &p, const SharedScene &S)
+{
+	if (!PARK) return;
+	volatile float *c = S.park;
+	c[0 * RT_BLOCK_THREADS] = p.contrib.x; c[1 * RT_BLOCK_THREADS] = p.contrib.y; c[2 * RT_BLOCK_THREADS] = p.contrib.z;
+	c[3 * RT_BLOCK_THREADS] = p.result.x;  c[4 * RT_BLOCK_THREADS] = p.result.y;  c[5 * RT_BLOCK_THREADS] = p.result.z;
+}
+
+template <bool PARK>
+__device__ __forceinline__ void path_unpark(Path &p, const SharedScene &S)
+{
+	if (!PARK) return;
+	volatile float *c = S.park;
+	p.contrib = mk(c[0 * RT_BLOCK_THREADS], c[1 * RT_BLOCK_THREADS], c[2 * RT_BLOCK_THREADS]);
+	p.result = mk(c[3 * RT_BLOCK_THREADS], c[4 * RT_BLOCK_THREADS], c[5 * RT_BLOCK_THREADS]);
+}
 __device__ __forceinline__ void stack_init(LocalStack &, const SharedScene &) {}
 
 /*
@@ -244,10 +274,10 @@ __device__ __forceinline__ void stack_init(LocalStack &, const SharedScene &) {}
 #define RT_WALK_ITERS 8
 #endif
 #ifndef RT_WALK_HOLD
-#define RT_WALK_HOLD 16     /* 8: +3 %, 1 (no waiting): +17 % on BASELINE config 5 */
+#define RT_WALK_HOLD 12     /* 4K config 5: 8 / 12 / 16 / 20 lanes: +3 % / 31.4 / 31.7 / 32.7 ms; 1 (no waiting): +17 % */
 #endif
 
-template <bool LBVH, bool DEFER_SKY, class Stack>
+template <bool LBVH, bool DEFER_SKY, bool PARK = false, class Stack>
 __device__ __forceinline__ unsigned warp_step(Path &p, Walk &w, Stack &st, const RtRenderParams &P, const SharedScene &S)
 {
 	unsigned traced = 0;
@@ -295,6 +325,7 @@ __device__ __forceinline__ unsigned warp_step(Path &p, Walk &w, Stack &st, const
 		const unsigned hits = __ballot_sync(full, p.mode == MODE_HIT);
 		if (hits == 0) return traced;
 		if (__popc(hits) < RT_WALK_HOLD && __any_sync(full, p.mode == MODE_WALK)) return traced;
+		path_unpark<PARK>(p, S);
 		if (p.mode == MODE_HIT)
 			path_classify<DEFER_SKY>(p, w.best, dn, P.scene, P.sky, S.lut,
 			              [&](const Hit &hh, f3 d, f3 &point, f3 &normal) {
@@ -303,6 +334,7 @@ __device__ __forceinline__ unsigned warp_step(Path &p, Walk &w, Stack &st, const
 	}
 	warp_sweep_cached(p, S.sweep, S.dirs);
 	if (p.mode == MODE_LAUNCH) path_launch(p, P.scene, S.dirs + (threadIdx.x & 31) * RT_DIR_ROW);
+	path_park<LBVH && PARK>(p, S);
 	return traced;
 }
 
@@ -360,6 +392,7 @@ __global__ void __launch_bounds__(RT_BLOCK_THREADS, TRAV ? RT_LBVH_MIN_BLOCKS : 
 render_persistent_kernel(const __grid_constant__ RtRenderParams P)
 {
 	constexpr bool LBVH = TRAV != 0;
+	constexpr bool PARK = TRAV == 1 && RT_PARK_PATH;
 	extern __shared__ __align__(16) unsigned char smem[];
 	SharedScene S = stage_scene(P, smem, !LBVH);
 
@@ -382,6 +415,7 @@ render_persistent_kernel(const __grid_constant__ RtRenderParams P)
 	for (;;) {
 		unsigned idle = __ballot_sync(full, p.mode == MODE_IDLE);
 		if (idle) {
+			path_unpark<PARK>(p, S);
 			if (P.scale >= 4) {             /* warp-uniform */
 				store_cells_warp(P, p.mode == MODE_IDLE && owns, c, path_final(p));
 				if (p.mode == MODE_IDLE) owns = false;
@@ -418,12 +452,13 @@ render_persistent_kernel(const __grid_constant__ RtRenderParams P)
 				owns = true;
 			}
 			batch_next += min((unsigned) __popc(idle), avail);
+			path_park<PARK>(p, S);
 		}
 		if (__ballot_sync(full, p.mode != MODE_IDLE) == 0) {
 			if (exhausted && batch_next == batch_end) break;
 			continue;       /* only clipped cells were handed out; fetch more */
 		}
-		rays += warp_step<LBVH, false>(p, w, st, P, S);
+		rays += warp_step<LBVH, false, PARK>(p, w, st, P, S);
 	}
 	count_rays(P, rays);
 	walk_counters_flush(P, w);
@@ -737,7 +772,6 @@ __device__ __forceinline__ void wf_launch_slot(const WfPool &pool, int s, const 
 	p.shadow = (st & WF_SHADOW) != 0;
 	p.normal = pool.get3(WF_NORMAL, s);
 	p.point = pool.get3(WF_POINT, s);
-	p.to_light = pool.get3(WF_TOLIGHT, s);
 	const bool shade = p.pending == 0;
 	if (shade) {
 		p.obj = (int) pool.u(WF_OBJ, s);
@@ -774,7 +808,7 @@ render_wavefront_kernel(const __grid_constant__ RtRenderParams P)
 	extern __shared__ __align__(16) unsigned char smem[];
 	SharedScene S = stage_scene(P, smem, !LBVH);
 	size_t scene_bytes = RT_SCENE_HEAD_BYTES +
-	                     (LBVH ? sizeof(int) * (RT_SMEM_STACK + 1) * RT_BLOCK_THREADS
+	                     (LBVH ? sizeof(int) * (RT_SMEM_STACK + 1 + RT_PARK_WORDS) * RT_BLOCK_THREADS
 	                           : 2 * sizeof(float4) * (size_t) P.scene.n + sizeof(int2) * (size_t) P.scene.num_runs);
 	scene_bytes = (scene_bytes + 15) & ~(size_t) 15;
 	const unsigned full = 0xffffffffu;
@@ -898,7 +932,6 @@ render_wavefront_kernel(const __grid_constant__ RtRenderParams P)
 					pool.set3(WF_POINT, s, point);
 					pool.set3(WF_NORMAL, s, normal);
 					pool.set3(WF_SAMPLED, s, mk(0.0f, 0.0f, 0.0f));
-					if (lit) pool.set3(WF_TOLIGHT, s, sub3(mk(P.scene.light_pos), point));   /* main.c:184 */
 					/* got = 0, pending = 0; fresh asks the sweep phase for the three tests */
 					pool.u(WF_STATE, s) = (st & ~(3u | (3u << 8) | (7u << 10) | WF_FRESH)) | (unsigned) MODE_LAUNCH | (lit ? WF_FRESH : 0u);
 				}
@@ -1046,7 +1079,7 @@ __global__ void probe_div_kernel(uint64_t seed, unsigned per_thread, int lo_exp_
 static size_t smem_bytes(const RtRenderParams &P, bool lbvh)
 {
 	return RT_SCENE_HEAD_BYTES +
-	       (lbvh ? sizeof(int) * (RT_SMEM_STACK + 1) * RT_BLOCK_THREADS      /* traversal stacks */
+	       (lbvh ? sizeof(int) * (RT_SMEM_STACK + 1 + RT_PARK_WORDS) * RT_BLOCK_THREADS      /* traversal stacks, parked path state */
 	             : 2 * sizeof(float4) * (size_t) P.scene.n + sizeof(int2) * (size_t) P.scene.num_runs);
 }
 
