@@ -11,7 +11,7 @@
 
 #define RT_BVH_STACK 64
 #ifndef RT_SMEM_STACK
-#define RT_SMEM_STACK 32         /* traversal-stack entries per thread in shared memory (config 5: depth 13 used); deeper trees use the local-memory build */
+#define RT_SMEM_STACK 32         /* traversal-stack entries per thread in shared memory (config 5: tree depth 22, 13 entries used); deeper trees use the local-memory build */
 #endif
 #define RT_TILE_W 8           /* a warp covers an 8x4 tile of low-res pixels */
 #define RT_TILE_H 4

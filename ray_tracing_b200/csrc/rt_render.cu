@@ -310,6 +310,8 @@ __device__ __forceinline__ unsigned warp_step(Path &p, Walk &w, Stack &st, const
 		}
 		const bool walking = p.mode == MODE_WALK;
 		const f3 ro = p.ray_o, dn = p.ray_d;
+		/* (the ray's slab constants are re-derived every step: parking them in shared memory per
+		 * ray was measured, 31.0 vs 30.5 ms -- the arithmetic is off the ALU pipe that bounds the walk) */
 		if (walking) walk_nodes(P.bvh, walk_ray(P.bvh, ro, dn), w, st, RT_WALK_ITERS);
 		__syncwarp();
 		int prim = 0;
