@@ -541,6 +541,15 @@ class GpuBench:
             if want is not None:
                 out["frame_matches_reference"] = out["frame_sha256"] == want
         self.launches += launches * (steps + max(warmup, 3))
+        if cfg["kind"] == "sweep" and self.world == 1:
+            # the same sweeps with the passes one after the other (what every sweep did before the
+            # concurrent sweep, and what ranks of a multi-GPU run still do), for the record
+            self.r.set_concurrent_sweep(False)
+            sms, _ = self.time_steps(step, finish, max(steps // 2, 5), 3)
+            self.r.set_concurrent_sweep(True)
+            self.launches += launches * (max(steps // 2, 5) + 3)
+            out["schedule"] = "the five passes run side by side on separate streams, one resolve kernel folds them in pass order (rt_api.cu: sweep_concurrent)"
+            out["passes_one_after_the_other"] = {"ms_per_step": sms, "frames_per_s": 1e3 / sms}
         return out, (step, finish, to_host, rays, my_rays)
 
 
@@ -628,7 +637,7 @@ def main_gpu(args):
             r.set_tile_schedule(schedule)
             ms = []
             for i in range(8):
-                cam = host.Camera((5.0 + 0.03 * (i + 1) + (0.5 if schedule else 0.0), 5.0, 5.0), (-1.0, -1.0, -1.0), (0, 1, 0), 30.0)
+                cam = host.Camera((5.0 + 0.03 * (i + 1), 5.0, 5.0), (-1.0, -1.0, -1.0), (0, 1, 0), 30.0)   # the same poses both ways; toggling the schedule forgets them
                 for sc in (8, 4, 2):
                     r.render_into(cam, local.data_ptr(), W, H, stats=True, scale=sc, pass_index=0, variant=b.variant, kernel=b.kernel)
                 ms.append(r.render_into(cam, local.data_ptr(), W, H, stats=True, scale=1, pass_index=0, variant=b.variant, kernel=b.kernel)["render_ms"])

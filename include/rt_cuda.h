@@ -336,6 +336,15 @@ int rt_cuda_debug_set_sweep_threshold(float tau2);
  * repeatedly is scheduled longest tiles first from the costs its previous pass recorded.
  * Scheduling only: frames must be identical either way. */
 int rt_cuda_debug_set_tile_schedule(int on);
+/* Test knob, LBVH scenes: 1 (default) = when ONE object of the scene emits, a light sample
+ * (main.c:186-205) is walked in any-hit mode -- the emitter first, then only until something is
+ * accepted in front of it -- because all the sample adds is the emission of its nearest hit
+ * (main.c:201-204); 0 = every ray is walked to its nearest hit.  Frames must be identical. */
+int rt_cuda_debug_set_light_anyhit(int on);
+/* Test knob: 1 (default) = rt_cuda_render_sweep() on one GPU runs the passes of the sweep side by
+ * side on separate streams and folds them into the frame in pass order with one resolve kernel;
+ * 0 = one pass after the other.  Frames, accumulation and ray counts must be identical. */
+int rt_cuda_debug_set_concurrent_sweep(int on);
 /* Unit probe of the longest-tiles-first order: tiles_x*tiles_y tiles ordered by the costs of a map
  * that is 1 << shift times coarser (stable: costly classes first, image order within a class). */
 int rt_cuda_debug_tile_order(const uint32_t *cost, int cost_tiles_x, int cost_tiles_y, int shift,

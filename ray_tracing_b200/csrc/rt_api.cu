@@ -68,6 +68,7 @@ extern "C" const char *rt_cuda_last_error(void) { return g_err; }
 
 #define RT_MAX_GPUS 16
 #define RT_WORK_SLOTS 8       /* tile counters: launches that may be in flight at once on one GPU */
+#define RT_SWEEP_MAX_COARSE 6 /* passes of a sweep above scale 1 (init_scale <= 64) */
 
 /* What the tile costs of a pose are valid for: the same scene seen from the same
  * camera through the same frame, band and interleave -- at any scale. */
@@ -120,6 +121,11 @@ struct DeviceCtx {
 	size_t       stage_bytes[2] = {0, 0};
 	cudaEvent_t  stage_rendered[2] = {nullptr, nullptr}, stage_copied[2] = {nullptr, nullptr};
 	int          stage_next = 0;
+	/* concurrent sweep (sweep_concurrent): side streams for the coarse passes, their cell buffers */
+	cudaStream_t sweep_stream[RT_SWEEP_MAX_COARSE] = {};
+	cudaEvent_t  sweep_fork = nullptr, sweep_join[RT_SWEEP_MAX_COARSE] = {};
+	float       *sweep_cells = nullptr;   size_t sweep_cells_floats = 0;
+	float       *sweep_fine = nullptr;    size_t sweep_fine_floats = 0;     /* the scale-1 pass, W x H float3 */
 };
 
 struct Context {
@@ -138,6 +144,7 @@ struct Context {
 	float     sweep_tau2 = 4e-12f;      /* rt_device.cuh: sample_faces_surface; tests may override */
 	unsigned  scene_epoch = 0;          /* bumped by every scene upload (tile schedules die with the scene) */
 	int       tile_schedule = 1;        /* 0: never reorder tiles (tests / A-B) */
+	int       concurrent_sweep = 1;     /* 0: rt_cuda_render_sweep runs its passes one after the other (tests / A-B) */
 };
 
 static Context g;
@@ -169,6 +176,12 @@ static void free_device(DeviceCtx &d)
 		if (d.stage_copied[k]) cudaEventDestroy(d.stage_copied[k]);
 	}
 	if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
+	for (int k = 0; k < RT_SWEEP_MAX_COARSE; k++) {
+		if (d.sweep_stream[k]) cudaStreamDestroy(d.sweep_stream[k]);
+		if (d.sweep_join[k]) cudaEventDestroy(d.sweep_join[k]);
+	}
+	if (d.sweep_fork) cudaEventDestroy(d.sweep_fork);
+	cudaFree(d.sweep_cells); cudaFree(d.sweep_fine);
 	if (d.stream) cudaStreamDestroy(d.stream);
 	d = DeviceCtx();
 }
@@ -891,10 +904,18 @@ static void tile_schedule_done(DeviceCtx &d, const RtRenderParams &P, int scale,
 }
 
 /* Launch one pass for one device over output rows [r0, r1) (scale aligned). */
+struct LaunchExtra {
+	bool  compact = false;       /* one value per low-res cell instead of the replicated tiles (RtRenderParams::compact) */
+	bool  no_schedule = false;   /* leave the pose's tile schedule alone (launches that overlap one another) */
+	float grid_share = 1.0f;     /* persistent kernels: fraction of the resident CTA slots this launch may take */
+};
+
 static int launch_band(DeviceCtx &d, const RtCamera *cam, const PassPlan &pl, const RtRenderOpts *o,
                        void *fb, int fb_row_offset, int r0, int r1, int il_n, int il_i, cudaStream_t stream,
-                       bool accumulate, float accum_weight, float inv_count, int *launches)
+                       bool accumulate, float accum_weight, float inv_count, int *launches, const LaunchExtra *extra = nullptr)
 {
+	const LaunchExtra none;
+	const LaunchExtra &X = extra ? *extra : none;
 	RtRenderParams P;
 	memset(&P, 0, sizeof(P));
 	fill_views(d, P);
@@ -928,6 +949,9 @@ static int launch_band(DeviceCtx &d, const RtCamera *cam, const PassPlan &pl, co
 	P.fb = fb;
 	P.fb_format = o->fb_format;
 	P.fb_row_offset = fb_row_offset;
+	P.compact = X.compact ? 1 : 0;
+	P.store_scale = X.compact ? 1 : pl.scale;
+	P.store_stride = X.compact ? P.cells_per_row : pl.w;
 	P.accum = accumulate ? d.accum : nullptr;
 	P.accum_row_offset = d.accum_row0;
 	P.accum_weight = accum_weight;
@@ -936,7 +960,7 @@ static int launch_band(DeviceCtx &d, const RtCamera *cam, const PassPlan &pl, co
 	/* pixels the reference's pass never writes hold 0 (clear_uncovered_owned) */
 	int covered_rows_end = std::min(P.lh * pl.scale, r1);
 	bool columns_uncovered = P.column_w * pl.ncols < pl.w;
-	if (covered_rows_end < r1 || columns_uncovered) {
+	if (!X.compact && (covered_rows_end < r1 || columns_uncovered)) {
 		int rc = clear_uncovered_owned(fb, pl, fb_row_offset, P.il_n, P.il_i, bytes_per_pixel(o->fb_format),
 		                               covered_rows_end, columns_uncovered, stream, launches);
 		if (rc != RT_OK) return rc;
@@ -974,10 +998,11 @@ static int launch_band(DeviceCtx &d, const RtCamera *cam, const PassPlan &pl, co
 			}
 			unsigned warps_needed = (unsigned) P.tiles_x * P.tiles_y;
 			unsigned blocks_needed = (warps_needed + (RT_BLOCK_THREADS / 32) - 1) / (RT_BLOCK_THREADS / 32);
-			grid = (int) std::min<unsigned>((unsigned) (d.sm_count * per_sm), blocks_needed);
+			unsigned slots = (unsigned) std::max(1, (int) ((float) (d.sm_count * per_sm) * X.grid_share));
+			grid = (int) std::min<unsigned>(slots, blocks_needed);
 		}
 		bool sched = false;
-		if (pl.queued) {
+		if (pl.queued && !X.no_schedule) {
 			TileKey key;
 			memset(&key, 0, sizeof(key));
 			key.w = pl.w; key.h = pl.h; key.ncols = pl.ncols; key.r0 = r0; key.r1 = r1;
@@ -1014,18 +1039,9 @@ static int validate_common(const RtCamera *cam, void *fb, int w, int h, const Rt
 	return RT_OK;
 }
 
-/* ship = false: a pass of a sweep whose frame nobody will look at (only the accumulation
- * matters): a rank with a remote frame renders it locally and sends nothing */
-static int render_pass(const RtCamera *cam, void *fb, int w, int h, const RtRenderOpts *o,
-                       bool accumulate, RtRenderStats *stats, bool sync_and_copy, bool ship = true)
+/* traversal, build and kernel of a pass (pl.w, pl.h, pl.scale set by the caller) */
+static int plan_kernel(PassPlan &pl, const RtRenderOpts *o)
 {
-	PassPlan pl;
-	pl.w = w; pl.h = h; pl.scale = o->scale; pl.ncols = o->num_columns;
-	pl.row0 = o->row_begin; pl.row1 = o->row_end;
-	if (pl.row0 == 0 && pl.row1 == 0) pl.row1 = h;
-	if (pl.row0 < 0 || pl.row1 > h || pl.row0 >= pl.row1) return fail(RT_ERR_ARG, "bad row band [%d,%d)", pl.row0, pl.row1);
-	if (pl.row0 % pl.scale != 0 || (pl.row1 % pl.scale != 0 && pl.row1 != h))
-		return fail(RT_ERR_ARG, "row band must be aligned to scale");
 	int rc = pick_traversal(o->traversal, &pl.lbvh);
 	if (rc != RT_OK) return rc;
 	pl.exact = o->variant == RT_VARIANT_EXACT;
@@ -1042,8 +1058,26 @@ static int render_pass(const RtCamera *cam, void *fb, int w, int h, const RtRend
 		pl.persistent = true;
 	}
 	/* the wavefront kernel packs the tile width into 5 bits and a pixel's x, y into 16 bits each */
-	if (pl.wavefront && (o->scale > 31 || w > 65535 || h > 65535))
+	if (pl.wavefront && (o->scale > 31 || pl.w > 65535 || pl.h > 65535))
 		return fail(RT_ERR_ARG, "RT_KERNEL_WAVEFRONT supports scale <= 31 and frames up to 65535x65535");
+
+	return RT_OK;
+}
+
+/* ship = false: a pass of a sweep whose frame nobody will look at (only the accumulation
+ * matters): a rank with a remote frame renders it locally and sends nothing */
+static int render_pass(const RtCamera *cam, void *fb, int w, int h, const RtRenderOpts *o,
+                       bool accumulate, RtRenderStats *stats, bool sync_and_copy, bool ship = true)
+{
+	PassPlan pl;
+	pl.w = w; pl.h = h; pl.scale = o->scale; pl.ncols = o->num_columns;
+	pl.row0 = o->row_begin; pl.row1 = o->row_end;
+	if (pl.row0 == 0 && pl.row1 == 0) pl.row1 = h;
+	if (pl.row0 < 0 || pl.row1 > h || pl.row0 >= pl.row1) return fail(RT_ERR_ARG, "bad row band [%d,%d)", pl.row0, pl.row1);
+	if (pl.row0 % pl.scale != 0 || (pl.row1 % pl.scale != 0 && pl.row1 != h))
+		return fail(RT_ERR_ARG, "row band must be aligned to scale");
+	int rc = plan_kernel(pl, o);
+	if (rc != RT_OK) return rc;
 
 	size_t bpp = bytes_per_pixel(o->fb_format);
 	int band_rows = pl.row1 - pl.row0;
@@ -1280,6 +1314,247 @@ extern "C" int render_frame_cuda(const RtScene *scene, const RtCamera *cam, void
 	return render_pass(cam, fb, w, h, &o, false, nullptr, true);
 }
 
+/* ------------------------------------------------------ concurrent sweep */
+
+/*
+ * The passes of a progressive sweep (main.c:354, 402-403: scale 16, 8, 4, 2, 1 after an
+ * invalidation) are independent path-tracing jobs -- each has its own RNG key (pass index) and
+ * its own pixel grid -- and the coarse ones are tiny: 8 040 paths at scale 16 of a 1080p frame,
+ * which keep 1/14 of the GPU busy for as long as their longest path lasts (up to 40 dependent
+ * rays, ~0.15 ms).  Run one after the other the five passes take 1.28 ms, of which the three
+ * coarsest are 0.45 ms of a nearly idle GPU.  What orders them is only the accumulation
+ * (main.c:394: accum = accum * 1 + column_data / scale^2, a binary32 sum taken in pass order).
+ *
+ * So: every coarse pass runs on its own stream and writes ONE value per low-res cell
+ * (RtRenderParams::compact) into its own small buffer, the scale-1 pass writes a plain frame,
+ * all five side by side; then one resolve kernel folds them per output pixel in pass order --
+ * the same additions main.c:394 performs (weights are powers of two, a pixel a pass does not
+ * cover adds nothing: rows >= (H / scale) * scale, main.c:285-290) -- and writes the
+ * accumulation buffer and the resolved frame (main.c:476).  Bit-identical to the sequential
+ * passes (tests/test_gpu_parity.py: sweeps vs the oracle), which stay as the path for
+ * several GPUs, row bands and the other kernels.
+ */
+struct SweepCoarse {
+	const float *cells;       /* cells_per_row x lh float3 */
+	int   scale, lh, cells_per_row, cells_per_col;
+	float weight;             /* 1.0f / (scale * scale) */
+};
+struct SweepResolve {
+	SweepCoarse coarse[RT_SWEEP_MAX_COARSE];
+	int   ncoarse;
+	const float *fine;        /* scale-1 pass: W x H float3 */
+	float *accum;
+	void  *fb;
+	int    fb_format;
+	int    W, H, column_w, covered_w;
+	float  inv_count;
+};
+
+__global__ void __launch_bounds__(256) sweep_resolve_kernel(const __grid_constant__ SweepResolve R)
+{
+	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+	if (x >= R.W) return;
+	const size_t p = (size_t) y * R.W + x;
+	float ax = 0.0f, ay = 0.0f, az = 0.0f;
+	if (x < R.covered_w) {            /* main.c:363: columns beyond T * column_w are never rendered */
+		const int col = x / R.column_w, xi = x - col * R.column_w;
+		for (int k = 0; k < R.ncoarse; k++) {
+			const SweepCoarse &c = R.coarse[k];
+			const int j = y / c.scale;
+			if (j >= c.lh) continue;                                   /* main.c:285-290 */
+			const float *v = c.cells + 3 * ((size_t) j * c.cells_per_row + col * c.cells_per_col + xi / c.scale);
+			ax = __fadd_rn(ax, __fmul_rn(v[0], c.weight));             /* main.c:394 combine(accum, data, 1, 1/scale^2) */
+			ay = __fadd_rn(ay, __fmul_rn(v[1], c.weight));
+			az = __fadd_rn(az, __fmul_rn(v[2], c.weight));
+		}
+		const float *f = R.fine + 3 * p;
+		ax = __fadd_rn(ax, f[0]); ay = __fadd_rn(ay, f[1]); az = __fadd_rn(az, f[2]);
+	}
+	float *a = R.accum + 3 * p;
+	a[0] = ax; a[1] = ay; a[2] = az;
+	const float ox = __fmul_rn(ax, R.inv_count), oy = __fmul_rn(ay, R.inv_count), oz = __fmul_rn(az, R.inv_count);   /* main.c:476 */
+	if (R.fb_format == RT_FB_F32X3) {
+		float *o = reinterpret_cast<float *>(R.fb) + 3 * p;
+		o[0] = ox; o[1] = oy; o[2] = oz;
+	} else {
+		uchar4 q;                                                      /* main.c:666-670 */
+		q.x = (unsigned char) __float2uint_rz(__fmul_rn(ox, 255.0f));
+		q.y = (unsigned char) __float2uint_rz(__fmul_rn(oy, 255.0f));
+		q.z = (unsigned char) __float2uint_rz(__fmul_rn(oz, 255.0f));
+		q.w = 255;
+		if (x >= R.covered_w) q = make_uchar4(0, 0, 0, 0);             /* never written: the cleared frame (clear_uncovered_owned) */
+		reinterpret_cast<uchar4 *>(R.fb)[p] = q;
+	}
+}
+
+static bool sweep_can_run_concurrently(int w, int h, int init_scale, const RtRenderOpts &o)
+{
+	if (!g.concurrent_sweep || g.ngpu != 1 || init_scale < 2 || init_scale > 64) return false;
+	if (o.interleave_count > 1 || o.remote_fb || o.pipeline || o.frame_seq || o.band_only_fb) return false;
+	if (!((o.row_begin == 0 && o.row_end == 0) || (o.row_begin == 0 && o.row_end == h))) return false;
+	if (o.kernel == RT_KERNEL_WAVEFRONT || o.kernel == RT_KERNEL_PIXEL) return false;
+	(void) w;
+	return true;
+}
+
+/* CTA slots of the resident grid a coarse pass may take, so that the finer passes launched after it
+ * still find room: roughly the pass's share of the sweep's pixels, with a floor for the latency-bound
+ * coarsest ones.  The scale-1 pass comes last, asks for everything and soaks up what the others free. */
+static float sweep_grid_share(int scale)
+{
+	static float env[3] = {-1.0f, -1.0f, -1.0f};
+	if (env[0] < 0.0f) {
+		const char *e = getenv("RT_SWEEP_SHARES");      /* "s2,s4,coarser" for experiments */
+		if (!e || sscanf(e, "%f,%f,%f", &env[0], &env[1], &env[2]) != 3) { env[0] = 0.5f; env[1] = 0.25f; env[2] = 0.125f; }
+	}
+	return scale == 2 ? env[0] : (scale == 4 ? env[1] : env[2]);
+}
+
+static int sweep_concurrent(const RtCamera *cam, void *fb, int w, int h, int init_scale, uint64_t first_pass,
+                            const RtRenderOpts &o, RtRenderStats *stats, bool dev_fb)
+{
+	DeviceCtx &d = g.dev[0];
+	int rc = select_device(d);
+	if (rc != RT_OK) return rc;
+	cudaStream_t main_st = o.stream ? (cudaStream_t) o.stream : d.stream;
+	const size_t bpp = bytes_per_pixel(o.fb_format);
+	int launches = 0;
+
+	/* the passes */
+	int scales[RT_SWEEP_MAX_COARSE + 1], npass = 0;
+	for (int sc = init_scale; sc >= 1; sc >>= 1) scales[npass++] = sc;
+	const int ncoarse = npass - 1;
+
+	/* buffers: one cell grid per coarse pass, the scale-1 frame, the accumulation, a staging frame for a host fb */
+	const int ncols = o.num_columns, column_w = w / ncols;
+	size_t cell_off[RT_SWEEP_MAX_COARSE], cells_total = 0;
+	for (int k = 0; k < ncoarse; k++) {
+		int cpr = ncols * ((column_w + scales[k] - 1) / scales[k]), lh = h / scales[k];
+		cell_off[k] = cells_total;
+		cells_total += 3 * (size_t) cpr * lh;
+	}
+	if (d.sweep_cells_floats < cells_total) {
+		CU(cudaFree(d.sweep_cells));
+		d.sweep_cells = nullptr; d.sweep_cells_floats = 0;
+		CU(cudaMalloc(&d.sweep_cells, cells_total * sizeof(float)));
+		d.sweep_cells_floats = cells_total;
+	}
+	const size_t fine_floats = 3 * (size_t) w * h;
+	if (d.sweep_fine_floats < fine_floats) {
+		CU(cudaFree(d.sweep_fine));
+		d.sweep_fine = nullptr; d.sweep_fine_floats = 0;
+		CU(cudaMalloc(&d.sweep_fine, fine_floats * sizeof(float)));
+		d.sweep_fine_floats = fine_floats;
+	}
+	bool fresh = false;
+	if ((rc = ensure_accum(d, w, h, 0, h, &fresh)) != RT_OK) return rc;
+	d.accum_needs_clear = false;                    /* the resolve writes every pixel */
+	void *target = fb;
+	if (!dev_fb) {
+		size_t need = (size_t) w * h * bpp;
+		if (d.fb_bytes < need) {
+			CU(cudaFree(d.fb));
+			d.fb = nullptr; d.fb_bytes = 0;
+			CU(cudaMalloc(&d.fb, need));
+			d.fb_bytes = need;
+		}
+		target = d.fb;
+	}
+	if (!d.sweep_fork) CU(cudaEventCreateWithFlags(&d.sweep_fork, cudaEventDisableTiming));
+	for (int k = 0; k < ncoarse; k++) {
+		if (!d.sweep_stream[k]) CU(cudaStreamCreateWithFlags(&d.sweep_stream[k], cudaStreamNonBlocking));
+		if (!d.sweep_join[k]) CU(cudaEventCreateWithFlags(&d.sweep_join[k], cudaEventDisableTiming));
+	}
+
+	PassPlan pl;
+	pl.w = w; pl.h = h; pl.ncols = ncols; pl.row0 = 0; pl.row1 = h;
+	pl.scale = 1;
+	RtRenderOpts oo = o;
+	oo.scale = 1;
+	if ((rc = plan_kernel(pl, &oo)) != RT_OK) return rc;
+	if (pl.lbvh) {
+		float need = rt_lbvh_required_dmax(&d.bvh, cam->pos);
+		if (need > d.bvh.d_max && (rc = rt_lbvh_refit(&d.bvh, d.geomA, d.geomB, need * 1.05f, main_st)) != RT_OK)
+			return fail(rc, "LBVH refit failed: %s", rt_lbvh_last_error());
+	}
+
+	if (stats) {
+		CU(cudaMemsetAsync(d.ray_counter, 0, 4 * sizeof(unsigned long long), main_st));
+		CU(cudaEventRecord(d.ev[0], main_st));
+	}
+	CU(cudaEventRecord(d.sweep_fork, main_st));
+
+	SweepResolve R;
+	memset(&R, 0, sizeof(R));
+	float count = 0.0f;
+	uint64_t pixels = 0;
+	for (int k = 0; k < npass; k++) {
+		const int sc = scales[k];
+		const bool fine = sc == 1;
+		const float wgt = 1.0f / (float) (sc * sc);           /* main.c:278 */
+		count += wgt;                                          /* main.c:395 */
+		pl.scale = sc;
+		oo = o;
+		oo.scale = sc;
+		oo.pass_index = first_pass + (uint64_t) k;
+		oo.fb_format = RT_FB_F32X3;
+		oo.accumulate = 0;
+		LaunchExtra X;
+		X.no_schedule = true;
+		X.compact = !fine;
+		X.grid_share = fine ? 1.0f : sweep_grid_share(sc);
+		const int cpc = (column_w + sc - 1) / sc, cpr = ncols * cpc, lh = h / sc;
+		pixels += (uint64_t) cpr * (uint64_t) lh;
+		cudaStream_t st = fine ? main_st : d.sweep_stream[k];
+		void *out = fine ? (void *) d.sweep_fine : (void *) (d.sweep_cells + cell_off[k]);
+		if (!fine) CU(cudaStreamWaitEvent(st, d.sweep_fork, 0));
+		rc = launch_band(d, cam, pl, &oo, out, 0, 0, h, 1, 0, st, false, wgt, 1.0f, &launches, &X);
+		if (rc != RT_OK) return rc;
+		if (!fine) {
+			CU(cudaEventRecord(d.sweep_join[k], st));
+			SweepCoarse &c = R.coarse[k];
+			c.cells = d.sweep_cells + cell_off[k];
+			c.scale = sc; c.lh = lh; c.cells_per_row = cpr; c.cells_per_col = cpc; c.weight = wgt;
+		}
+	}
+	for (int k = 0; k < ncoarse; k++) CU(cudaStreamWaitEvent(main_st, d.sweep_join[k], 0));
+	R.ncoarse = ncoarse;
+	R.fine = d.sweep_fine;
+	R.accum = d.accum;
+	R.fb = target;
+	R.fb_format = o.fb_format;
+	R.W = w; R.H = h; R.column_w = column_w; R.covered_w = column_w * ncols;
+	g.accum_count = count;
+	R.inv_count = 1.0f / count;                                /* main.c:476 */
+	sweep_resolve_kernel<<<dim3((unsigned) ((w + 255) / 256), (unsigned) h), 256, 0, main_st>>>(R);
+	CU(cudaGetLastError());
+	launches++;
+	if (stats) CU(cudaEventRecord(d.ev[1], main_st));
+
+	/* with a caller stream, a device frame and no statistics the whole sweep is stream-ordered */
+	if (dev_fb && o.stream && !stats) return RT_OK;
+	if (stats) CU(cudaMemcpyAsync(d.host_rays, d.ray_counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, main_st));
+	float copy_ms = 0.0f;
+	if (!dev_fb) {
+		CU(cudaEventRecord(d.ev[2], main_st));
+		CU(cudaMemcpyAsync(fb, d.fb, (size_t) w * h * bpp, cudaMemcpyDeviceToHost, main_st));
+		CU(cudaEventRecord(d.ev[3], main_st));
+	}
+	CU(cudaStreamSynchronize(main_st));
+	if (stats) {
+		memset(stats, 0, sizeof(*stats));
+		float ms = 0.0f;
+		CU(cudaEventElapsedTime(&ms, d.ev[0], d.ev[1]));
+		if (!dev_fb) CU(cudaEventElapsedTime(&copy_ms, d.ev[2], d.ev[3]));
+		stats->rays = *d.host_rays;
+		stats->pixels = pixels;
+		stats->render_ms = ms;
+		stats->copy_ms = copy_ms;
+		stats->kernel_launches = launches;
+	}
+	return RT_OK;
+}
+
 extern "C" int rt_cuda_render_sweep(const RtCamera *cam, void *fb, int w, int h, int init_scale,
                                     uint64_t first_pass, const RtRenderOpts *opts, RtRenderStats *stats)
 {
@@ -1300,6 +1575,7 @@ extern "C" int rt_cuda_render_sweep(const RtCamera *cam, void *fb, int w, int h,
 	memset(&total, 0, sizeof(total));
 	uint64_t pass = first_pass;
 	bool dev_fb = o.fb_memory == RT_MEM_DEVICE || (o.fb_memory == RT_MEM_AUTO && is_device_pointer(fb));
+	if (sweep_can_run_concurrently(w, h, init_scale, o)) return sweep_concurrent(cam, fb, w, h, init_scale, first_pass, o, stats, dev_fb);
 	for (int s = init_scale; s >= 1; s >>= 1, pass++) {             /* main.c:402-403 */
 		o.scale = s;
 		o.pass_index = pass;
@@ -1694,6 +1970,20 @@ extern "C" int rt_cuda_debug_set_tile_schedule(int on)
 {
 	g.tile_schedule = on ? 1 : 0;
 	for (int i = 0; i < g.ngpu; i++) g.dev[i].sched.have_key = false;
+	return RT_OK;
+}
+
+/* Test / A-B knob: 0 = rt_cuda_render_sweep() runs its passes one after the other. */
+extern "C" int rt_cuda_debug_set_concurrent_sweep(int on)
+{
+	g.concurrent_sweep = on ? 1 : 0;
+	return RT_OK;
+}
+
+extern "C" void rt_lbvh_debug_set_anyhit(int on);
+extern "C" int rt_cuda_debug_set_light_anyhit(int on)
+{
+	rt_lbvh_debug_set_anyhit(on);
 	return RT_OK;
 }
 

@@ -89,6 +89,11 @@ struct RtRenderParams {
 	float    sweep_tau2;      /* rt_device.cuh: sample_faces_surface */
 
 	/* output */
+	int    compact;           /* 1: one value per low-res CELL, row-major over cells_per_row x lh (the concurrent
+	                           * sweep, rt_api.cu: the passes of a sweep run side by side and a resolve kernel folds
+	                           * them into the frame in pass order); 0: the tile replication of main.c:305-310 */
+	int    store_scale;       /* output pixels per cell side: scale, or 1 when compact */
+	int    store_stride;      /* pixels per output row: W, or cells_per_row when compact */
 	void  *fb;                /* RT_FB_F32X3: float[3] per pixel; RT_FB_U8X4: uchar4 */
 	int    fb_format;
 	int    fb_row_offset;     /* output row r is stored at fb row (r - fb_row_offset) */

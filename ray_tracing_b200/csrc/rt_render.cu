@@ -123,6 +123,7 @@ __device__ __forceinline__ Cell cell_geometry(const RtRenderParams &P, int cx, i
 	c.x0 = column_x + i * P.scale;
 	c.y0 = j * P.scale;
 	c.tw = min(P.scale, P.column_w - i * P.scale);
+	if (P.compact) { c.x0 = cx; c.y0 = j; c.tw = 1; }       /* warp-uniform */
 	return c;
 }
 
@@ -130,19 +131,19 @@ __device__ __forceinline__ Cell cell_geometry(const RtRenderParams &P, int cx, i
  * main.c:476 (resolve) when an accumulation buffer is attached. */
 __device__ __forceinline__ void store_cell(const RtRenderParams &P, const Cell &c, f3 color)
 {
-	for (int g = 0; g < P.scale; g++) {
+	for (int g = 0; g < P.store_scale; g++) {
 		int y = c.y0 + g;
 		for (int t = 0; t < c.tw; t++) {
 			int x = c.x0 + t;
 			f3 out = color;
 			if (P.accum) {
-				float *a = P.accum + 3 * ((size_t) (y - P.accum_row_offset) * P.W + x);
+				float *a = P.accum + 3 * ((size_t) (y - P.accum_row_offset) * P.store_stride + x);
 				f3 acc = mk(a[0] + color.x * P.accum_weight, a[1] + color.y * P.accum_weight,
 				            a[2] + color.z * P.accum_weight);
 				a[0] = acc.x; a[1] = acc.y; a[2] = acc.z;
 				out = scl3(acc, P.inv_count);
 			}
-			size_t p = (size_t) (y - P.fb_row_offset) * P.W + x;
+			size_t p = (size_t) (y - P.fb_row_offset) * P.store_stride + x;
 			if (P.fb_format == RT_FB_F32X3) {
 				float *f = reinterpret_cast<float *>(P.fb) + 3 * p;
 				f[0] = out.x; f[1] = out.y; f[2] = out.z;
@@ -164,12 +165,12 @@ __device__ __forceinline__ void store_pixel(const RtRenderParams &P, int x, int 
 {
 	f3 out = color;
 	if (P.accum) {
-		float *a = P.accum + 3 * ((size_t) (y - P.accum_row_offset) * P.W + x);
+		float *a = P.accum + 3 * ((size_t) (y - P.accum_row_offset) * P.store_stride + x);
 		f3 acc = mk(a[0] + color.x * P.accum_weight, a[1] + color.y * P.accum_weight, a[2] + color.z * P.accum_weight);
 		a[0] = acc.x; a[1] = acc.y; a[2] = acc.z;
 		out = scl3(acc, P.inv_count);
 	}
-	size_t p = (size_t) (y - P.fb_row_offset) * P.W + x;
+	size_t p = (size_t) (y - P.fb_row_offset) * P.store_stride + x;
 	if (P.fb_format == RT_FB_F32X3) {
 		float *f = reinterpret_cast<float *>(P.fb) + 3 * p;
 		f[0] = out.x; f[1] = out.y; f[2] = out.z;
@@ -198,7 +199,7 @@ __device__ __forceinline__ void store_cells_warp(const RtRenderParams &P, bool h
 		todo &= todo - 1;
 		int x0 = __shfl_sync(full, c.x0, src), y0 = __shfl_sync(full, c.y0, src), tw = __shfl_sync(full, c.tw, src);
 		f3 col = mk(__shfl_sync(full, color.x, src), __shfl_sync(full, color.y, src), __shfl_sync(full, color.z, src));
-		int n = tw * P.scale;
+		int n = tw * P.store_scale;
 		for (int i = lane; i < n; i += 32) {
 			int g = i / tw, t = i - g * tw;
 			store_pixel(P, x0 + t, y0 + g, col);
@@ -418,7 +419,7 @@ render_persistent_kernel(const __grid_constant__ RtRenderParams P)
 		unsigned idle = __ballot_sync(full, p.mode == MODE_IDLE);
 		if (idle) {
 			path_unpark<PARK>(p, S);
-			if (P.scale >= 4) {             /* warp-uniform */
+			if (P.store_scale >= 4) {       /* warp-uniform */
 				store_cells_warp(P, p.mode == MODE_IDLE && owns, c, path_final(p));
 				if (p.mode == MODE_IDLE) owns = false;
 			} else if (p.mode == MODE_IDLE && owns) {
@@ -533,7 +534,7 @@ __device__ __forceinline__ void rq_drain(const RtRenderParams &P, const SharedSc
 		 * long tiles first (sky tiles, cost 0, never touch the counter) */
 		if (P.tile_cost && RQ_BOUNCES(flags)) atomicMax(P.tile_cost + RQ_TILE(flags), RQ_BOUNCES(flags));
 	}
-	if (P.scale >= 4) store_cells_warp(P, has, c, color);   /* warp-uniform */
+	if (P.store_scale >= 4) store_cells_warp(P, has, c, color);   /* warp-uniform */
 	else if (has) store_cell(P, c, color);
 }
 

@@ -146,6 +146,8 @@ EXPORTED_SYMBOLS = [
     "rt_cuda_debug_div_check",
     "rt_cuda_debug_set_sweep_threshold",
     "rt_cuda_debug_set_tile_schedule",
+    "rt_cuda_debug_set_light_anyhit",
+    "rt_cuda_debug_set_concurrent_sweep",
     "rt_cuda_param_bytes",
     "rt_cuda_set_progressive",
     "rt_cuda_invalidate_accumulation",
@@ -224,6 +226,8 @@ def load_library() -> C.CDLL:
     L.rt_cuda_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.rt_cuda_debug_set_sweep_threshold.argtypes = [C.c_float]
     L.rt_cuda_debug_set_tile_schedule.argtypes = [C.c_int]
+    L.rt_cuda_debug_set_light_anyhit.argtypes = [C.c_int]
+    L.rt_cuda_debug_set_concurrent_sweep.argtypes = [C.c_int]
     L.rt_cuda_gl_register_buffer.argtypes = [C.c_uint, C.c_size_t]
     L.rt_cuda_gl_update_frame.argtypes = [C.POINTER(RtCamera), C.c_int, C.c_int, C.c_double, C.POINTER(RtRenderOpts), C.POINTER(RtRenderStats)]
     L.rt_cuda_gl_render_frame.argtypes = [C.POINTER(RtCamera), C.c_int, C.c_int, C.POINTER(RtRenderOpts), C.POINTER(RtRenderStats)]
@@ -643,6 +647,12 @@ class Renderer:
 
     def set_tile_schedule(self, on: bool) -> None:
         _check(self.lib.rt_cuda_debug_set_tile_schedule(1 if on else 0))
+
+    def set_concurrent_sweep(self, on: bool) -> None:
+        _check(self.lib.rt_cuda_debug_set_concurrent_sweep(1 if on else 0))
+
+    def set_light_anyhit(self, on: bool) -> None:
+        _check(self.lib.rt_cuda_debug_set_light_anyhit(1 if on else 0))
 
     def debug_tile_order(self, cost: np.ndarray, shift: int, tiles_x: int, tiles_y: int) -> np.ndarray:
         cost = np.ascontiguousarray(cost, dtype=np.uint32)

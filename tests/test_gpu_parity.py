@@ -341,6 +341,47 @@ def test_progressive_sweep_vs_oracle(renderer, port, small_sky, builtin_objects)
     assert renderer.accum_count() == 0.0
 
 
+def test_concurrent_sweep_equals_sequential_passes(renderer, small_sky, builtin_objects):
+    """rt_cuda_render_sweep on one GPU runs the passes of a sweep side by side and folds them in
+    pass order with one resolve kernel (rt_api.cu: sweep_concurrent).  Frame, accumulation
+    (checked through one more accumulated pass), weight and ray count must equal the
+    one-pass-after-the-other path: column counts that leave pixels uncovered (W % T != 0), sizes
+    whose last rows the coarse passes never write, every init scale, the 8-bit frame format,
+    a device frame on a caller's stream without statistics."""
+    import torch
+
+    renderer.upload_skybox(small_sky)
+    cases = [(0, 192, 108, 16, 1), (0, 200, 113, 16, 7), (1, 161, 97, 8, 3), (2, 128, 72, 4, 1), (0, 96, 54, 2, 5), (1, 322, 182, 4, 4)]
+    try:
+        for scene, W, H, init, cols in cases:
+            renderer.upload_scene(builtin_objects[scene])
+            got = {}
+            for on in (True, False):
+                renderer.set_concurrent_sweep(on)
+                frame, st = renderer.render_sweep(Camera(), W, H, init, first_pass=3, num_columns=cols)
+                count = renderer.accum_count()
+                nxt, _ = renderer.render_frame(Camera(), W, H, 1, pass_index=40, accumulate=1, num_columns=cols)
+                u8, _ = renderer.render_sweep(Camera(), W, H, init, first_pass=3, num_columns=cols, fb_format=RT_FB_U8X4)
+                got[on] = (frame, st["rays"], st["pixels"], count, nxt, u8)
+            a, b = got[True], got[False]
+            assert np.array_equal(bits(a[0]), bits(b[0])), (scene, W, H, init, cols)
+            assert a[1] == b[1] and a[2] == b[2] and a[3] == b[3]
+            assert np.array_equal(bits(a[4]), bits(b[4])), "the accumulation buffers differ"
+            assert np.array_equal(a[5], b[5])
+        # stream-ordered: device frame, caller's stream, no statistics
+        W, H = 192, 108
+        renderer.upload_scene(builtin_objects[0])
+        renderer.set_concurrent_sweep(True)
+        want, _ = renderer.render_sweep(Camera(), W, H, 16, first_pass=0)
+        dev = torch.full((H, W, 3), -1.0, dtype=torch.float32, device="cuda")
+        stream = torch.cuda.Stream()
+        renderer.render_sweep(Camera(), W, H, 16, first_pass=0, ptr=dev.data_ptr(), stats=False, stream=stream.cuda_stream)
+        stream.synchronize()
+        assert np.array_equal(bits(dev.cpu().numpy()), bits(want))
+    finally:
+        renderer.set_concurrent_sweep(True)
+
+
 def test_update_frame_loop_matches_reference_scheduler(renderer, port, small_sky, builtin_objects):
     """rt_cuda_update_frame / rt_cuda_invalidate_accumulation reproduce the
     workers' schedule (main.c:354, 402-408): init_scale, halving per published
@@ -580,6 +621,37 @@ def test_lbvh_equals_linear_scan_frames(renderer, small_sky):
     for kern in (RT_KERNEL_WAVEFRONT, RT_KERNEL_QUEUED):
         c, sc = renderer.render_frame(Camera(), 480, 270, 1, traversal=RT_TRAVERSAL_LBVH, kernel=kern)
         assert np.array_equal(bits(a), bits(c)) and sa["rays"] == sc["rays"]
+
+
+def test_light_samples_anyhit_changes_nothing(renderer, port, small_sky):
+    """Light samples are walked in any-hit mode when the scene has exactly one emitter
+    (rt_render.cu: warp_step).  Frames and ray counts must not depend on it: one emitter in the
+    middle of the index range (ties go to lower AND higher indices), an emitting cube among
+    cubes and spheres, two emitters (the mode must switch itself off), no emitter."""
+    W, H = 320, 180
+    renderer.upload_skybox(small_sky)
+    cases = []
+    cases.append(random_scene(1024, 77, spheres_only=True, extent=10.0))
+    mixed = random_scene(600, 12, extent=7.0)
+    mixed["type"][300] = 0
+    mixed["geom"][300] = (-1.0, 6.0, -1.0, 2.0, 0.5, 2.0)          # the emitter (index 300) as a slab above the scene
+    cases.append(mixed)
+    two = random_scene(500, 13, spheres_only=True, extent=6.0)
+    two["emission_power"][7] = 2.0
+    two["emission_color"][7] = (1.0, 0.5, 0.25)
+    cases.append(two)
+    cases.append(random_scene(300, 14, spheres_only=True, extent=5.0, emissive=False))
+    try:
+        for objs in cases:
+            renderer.upload_scene(objs)
+            want, rays = port.render(port.world(objs, small_sky), W, H, 1, 1, 0)
+            for on in (True, False):
+                renderer.set_light_anyhit(on)
+                for kern in (RT_KERNEL_AUTO, RT_KERNEL_QUEUED, RT_KERNEL_PIXEL):
+                    got, st = renderer.render_frame(Camera(), W, H, 1, traversal=RT_TRAVERSAL_LBVH, kernel=kern)
+                    assert np.array_equal(bits(got), bits(want)) and st["rays"] == rays, (on, kern)
+    finally:
+        renderer.set_light_anyhit(True)
 
 
 def test_large_scene_lbvh_vs_oracle(renderer, port, small_sky):

@@ -39,7 +39,7 @@ def main():
          "queued": host.RT_KERNEL_QUEUED, "auto": host.RT_KERNEL_AUTO}
     r = host.Renderer(num_gpus=1)
     if a.no_anyhit:
-        host.load_library().rt_lbvh_debug_set_anyhit(0)
+        r.set_light_anyhit(False)
     r.upload_skybox(scenes.procedural_skybox(256, seed=11))
     r.upload_scene(host.parse_scene_string_large(scenes.synthetic_spheres_text(a.n)))
     cam = host.Camera()
