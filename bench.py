@@ -643,9 +643,9 @@ def main_gpu(args):
                 ms.append(r.render_into(cam, local.data_ptr(), W, H, stats=True, scale=1, pass_index=0, variant=b.variant, kernel=b.kernel)["render_ms"])
             r.set_tile_schedule(True)
             return float(np.median(ms))
-        seeded, plain = fresh_pose_scale1_ms(True), fresh_pose_scale1_ms(False)
-        moving = {"scale1_ms_seeded_by_scale2": seeded, "scale1_ms_image_order": plain,
-                  "note": "first scale-1 pass of a NEW pose (8 poses, median), preceded by its scale 8, 4, 2 passes as in update_frame(); device time of the pass"}
+        seeded, plain, recording = fresh_pose_scale1_ms(2), fresh_pose_scale1_ms(False), fresh_pose_scale1_ms(True)
+        moving = {"scale1_ms_seeded_by_scale2": seeded, "scale1_ms_image_order": plain, "scale1_ms_default": recording,
+                  "note": "first scale-1 pass of a NEW pose (8 poses, median), preceded by its scale 8, 4, 2 passes as in update_frame(); device time of the pass.  default = image order while recording the tile costs that order the pose's later scale-1 passes; seeded = ordered by the costs of the scale-2 pass (rt_cuda_debug_set_tile_schedule(2): measured slower, not the default)"}
 
     # ---- the other build of the same kernels, for the record (N=1 only) ----
     other = None

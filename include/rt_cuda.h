@@ -334,7 +334,9 @@ size_t rt_cuda_param_bytes(void);
 int rt_cuda_debug_set_sweep_threshold(float tau2);
 /* Test knob: 0 = RT_KERNEL_QUEUED keeps tiles in image order; 1 (default) = a pose rendered
  * repeatedly is scheduled longest tiles first from the costs its previous pass recorded.
- * Scheduling only: frames must be identical either way. */
+ * Scheduling only: frames must be identical either way.  2 = as 1, and a pass whose own scale has
+ * no costs yet is ordered by the costs a coarser pass of the pose recorded (measured: the first
+ * scale-1 pass of a new 4K pose takes 2.00 ms seeded by its scale-2 pass, 1.97 ms in image order). */
 int rt_cuda_debug_set_tile_schedule(int on);
 /* Test knob, LBVH scenes: 1 (default) = when ONE object of the scene emits, a light sample
  * (main.c:186-205) is walked in any-hit mode -- the emitter first, then only until something is

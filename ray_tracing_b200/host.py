@@ -645,8 +645,10 @@ class Renderer:
     def gl_unregister_buffer(self) -> None:
         _check(self.lib.rt_cuda_gl_unregister_buffer())
 
-    def set_tile_schedule(self, on: bool) -> None:
-        _check(self.lib.rt_cuda_debug_set_tile_schedule(1 if on else 0))
+    def set_tile_schedule(self, on) -> None:
+        """False / 0: tiles in image order; True / 1 (default): longest tiles first from the costs recorded at
+        the pass's own scale; 2: finer passes are also seeded by coarser ones."""
+        _check(self.lib.rt_cuda_debug_set_tile_schedule(2 if (on == 2 and on is not True) else (1 if on else 0)))
 
     def set_concurrent_sweep(self, on: bool) -> None:
         _check(self.lib.rt_cuda_debug_set_concurrent_sweep(1 if on else 0))

@@ -573,11 +573,14 @@ def test_tile_schedule_changes_nothing(renderer, port, small_sky, builtin_object
         W2, H2 = 1280, 720                # scale 4: 4050 tiles, above the ordering threshold from there on
         world2 = port.world(builtin_objects[0], small_sky, cam2.as_dict())
         big = torch.empty((H2, W2, 3), dtype=torch.float32, device="cuda")
-        for p_idx, s in enumerate((16, 8, 4, 2, 1, 1)):
-            big.fill_(-1.0)
-            st = renderer.render_into(cam2, big.data_ptr(), W2, H2, stats=True, scale=s, pass_index=p_idx, kernel=RT_KERNEL_QUEUED)
-            w2, r2 = port.render(world2, W2, H2, s, 1, p_idx)
-            assert np.array_equal(bits(big.cpu().numpy()), bits(w2)) and st["rays"] == r2, (s, p_idx)
+        oracle2 = [port.render(world2, W2, H2, s, 1, p_idx) for p_idx, s in enumerate((16, 8, 4, 2, 1, 1))]
+        for mode in (2, True):            # 2: finer passes seeded by coarser ones (the A/B mode); True: the default
+            renderer.set_tile_schedule(mode)
+            for p_idx, s in enumerate((16, 8, 4, 2, 1, 1)):
+                big.fill_(-1.0)
+                st = renderer.render_into(cam2, big.data_ptr(), W2, H2, stats=True, scale=s, pass_index=p_idx, kernel=RT_KERNEL_QUEUED)
+                w2, r2 = oracle2[p_idx]
+                assert np.array_equal(bits(big.cpu().numpy()), bits(w2)) and st["rays"] == r2, (mode, s, p_idx)
         # interleaved row blocks: each rank's launches build their own order
         full = want
         for rep in range(3):
