@@ -29,17 +29,23 @@ namespace RT_NS {
 /* ---------------------------------------------------------------- helpers */
 
 /* fixed part of a block's scene area: byte LUT, sweep lists, direction caches */
-#define RT_SCENE_HEAD_BYTES (256 * sizeof(float) + RT_BLOCK_THREADS + (RT_BLOCK_THREADS / 32) * RT_DIR_CACHE_BYTES)
-
 /* The walk's loop wants ~12 more registers than the 64 a thread has at 8 CTAs per SM (ray 6, plane
  * selectors 6, cull limit, node base); without them the compiler re-derives the selectors and the
  * limit for every visited node (10 of 69 instructions, all on the ALU pipe, which is what bounds
  * the walk).  What a path only touches between rays -- contrib and result -- therefore waits in
  * shared memory while the lane walks (persistent kernel over the LBVH only). */
+#ifndef RT_PARK_WORDS
 #define RT_PARK_WORDS 6
+#endif
+#define RT_PARK_BYTES (RT_PARK_WORDS * sizeof(float) * RT_BLOCK_THREADS)
+#ifndef RT_QUEUED_PARK
+#define RT_QUEUED_PARK 0      /* the same for the queued kernel over the shared-memory scene (experiment) */
+#endif
 #ifndef RT_PARK_PATH
 #define RT_PARK_PATH 1
 #endif
+
+#define RT_SCENE_HEAD_BYTES (256 * sizeof(float) + RT_BLOCK_THREADS + RT_PARK_BYTES + (RT_BLOCK_THREADS / 32) * RT_DIR_CACHE_BYTES)
 
 struct SharedScene {
 	float4 *A;
@@ -49,7 +55,7 @@ struct SharedScene {
 	float  *dirs;             /* per warp: direction cache of warp_sweep_cached() (RT_DIR_ROW floats per lane) */
 	int2   *runs;             /* type runs of the scene (rt_device.cuh: nearest_linear) */
 	int    *stack;            /* LBVH: this thread's traversal-stack column (rt_device.cuh: SharedStack) */
-	volatile float *park;     /* LBVH: this thread's column of RT_PARK_WORDS words behind the stacks (path_park / path_unpark) */
+	volatile float *park;     /* this thread's column of RT_PARK_WORDS words (path_park / path_unpark) */
 };
 
 /* `smem` = start of the scene area: kernels that keep per-warp queues in shared
@@ -60,11 +66,11 @@ __device__ __forceinline__ SharedScene stage_scene(const RtRenderParams &P, unsi
 	SharedScene s;
 	s.lut = reinterpret_cast<float *>(smem);
 	s.sweep = smem + 256 * sizeof(float) + 32 * (threadIdx.x >> 5);
+	s.park = reinterpret_cast<float *>(smem + 256 * sizeof(float) + RT_BLOCK_THREADS) + threadIdx.x;
 	s.dirs = reinterpret_cast<float *>(smem + RT_SCENE_HEAD_BYTES - (RT_BLOCK_THREADS / 32) * RT_DIR_CACHE_BYTES) + (threadIdx.x >> 5) * (32 * RT_DIR_ROW);
 	s.A = reinterpret_cast<float4 *>(smem + RT_SCENE_HEAD_BYTES);
 	s.B = s.A + 1;            /* records interleaved: A[2*i], B[2*i] are neighbours (one address per object) */
 	s.stack = reinterpret_cast<int *>(s.A) + threadIdx.x;   /* LBVH scenes stage no objects: the area holds the stacks */
-	s.park = reinterpret_cast<float *>(s.A) + (RT_SMEM_STACK + 1) * RT_BLOCK_THREADS + threadIdx.x;
 	s.runs = reinterpret_cast<int2 *>(s.A + (linear ? 2 * P.scene.n : 0));
 	for (int i = threadIdx.x; i < 256; i += blockDim.x) s.lut[i] = __ldg(&P.byte_lut[i]);
 	if (linear)
@@ -289,6 +295,7 @@ __device__ __forceinline__ unsigned warp_step(Path &p, Walk &w, Stack &st, const
 			RayQ q = ray_quadratic(dn);
 			Hit h = nearest_linear(S.A, S.B, S.runs, P.scene.num_runs, P.scene.n, ro, dn, q, P.scene.div_safe);
 			traced = 1;
+			path_unpark<PARK>(p, S);
 			path_classify<DEFER_SKY>(p, h, dn, P.scene, P.sky, S.lut,
 			              [&](const Hit &hh, f3 d, f3 &point, f3 &normal) {
 				              surface_of(hh, S.A[2 * hh.obj], S.B[2 * hh.obj], ro, d, point, normal);
@@ -337,7 +344,7 @@ __device__ __forceinline__ unsigned warp_step(Path &p, Walk &w, Stack &st, const
 	}
 	warp_sweep_cached(p, S.sweep, S.dirs);
 	if (p.mode == MODE_LAUNCH) path_launch(p, P.scene, S.dirs + (threadIdx.x & 31) * RT_DIR_ROW);
-	path_park<LBVH && PARK>(p, S);
+	path_park<PARK>(p, S);
 	return traced;
 }
 
@@ -558,6 +565,7 @@ render_queued_kernel(const __grid_constant__ RtRenderParams P)
 	const unsigned full = 0xffffffffu;
 	const unsigned lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
 	const unsigned total = (unsigned) (P.tiles_x * P.tiles_y) * 32u;
+	constexpr bool QPARK = !LBVH && RT_QUEUED_PARK;
 
 	Path p;
 	p.mode = MODE_IDLE;
@@ -576,6 +584,7 @@ render_queued_kernel(const __grid_constant__ RtRenderParams P)
 	for (;;) {
 		unsigned idle = __ballot_sync(full, p.mode == MODE_IDLE);
 		if (idle) {
+			path_unpark<QPARK>(p, S);
 			/* ---- finish: push the ended paths, drain when a full warp's worth waits ---- */
 			const bool ended = p.mode == MODE_IDLE && owns;
 			unsigned em = __ballot_sync(full, ended);
@@ -678,6 +687,7 @@ render_queued_kernel(const __grid_constant__ RtRenderParams P)
 				prep_n -= n;
 				__syncwarp();
 			}
+			path_park<QPARK>(p, S);
 		}
 		/* nothing runs and nothing is left to hand out: the launch is over for this warp */
 		const bool over = __ballot_sync(full, p.mode != MODE_IDLE) == 0;
@@ -688,7 +698,7 @@ render_queued_kernel(const __grid_constant__ RtRenderParams P)
 			__syncwarp();
 		}
 		if (over) break;
-		rays += warp_step<LBVH, true>(p, w, st, P, S);
+		rays += warp_step<LBVH, true, QPARK>(p, w, st, P, S);
 	}
 	count_rays(P, rays);
 	walk_counters_flush(P, w);
@@ -811,7 +821,7 @@ render_wavefront_kernel(const __grid_constant__ RtRenderParams P)
 	extern __shared__ __align__(16) unsigned char smem[];
 	SharedScene S = stage_scene(P, smem, !LBVH);
 	size_t scene_bytes = RT_SCENE_HEAD_BYTES +
-	                     (LBVH ? sizeof(int) * (RT_SMEM_STACK + 1 + RT_PARK_WORDS) * RT_BLOCK_THREADS
+	                     (LBVH ? sizeof(int) * (RT_SMEM_STACK + 1) * RT_BLOCK_THREADS
 	                           : 2 * sizeof(float4) * (size_t) P.scene.n + sizeof(int2) * (size_t) P.scene.num_runs);
 	scene_bytes = (scene_bytes + 15) & ~(size_t) 15;
 	const unsigned full = 0xffffffffu;
@@ -1082,7 +1092,7 @@ __global__ void probe_div_kernel(uint64_t seed, unsigned per_thread, int lo_exp_
 static size_t smem_bytes(const RtRenderParams &P, bool lbvh)
 {
 	return RT_SCENE_HEAD_BYTES +
-	       (lbvh ? sizeof(int) * (RT_SMEM_STACK + 1 + RT_PARK_WORDS) * RT_BLOCK_THREADS      /* traversal stacks, parked path state */
+	       (lbvh ? sizeof(int) * (RT_SMEM_STACK + 1) * RT_BLOCK_THREADS      /* traversal stacks */
 	             : 2 * sizeof(float4) * (size_t) P.scene.n + sizeof(int2) * (size_t) P.scene.num_runs);
 }
 
