@@ -16,7 +16,9 @@
  *
  * Conventions: every call returns RT_OK (0) or a negative RT_ERR_* code and
  * never aborts; rt_cuda_last_error() gives the message.  All structs are POD.
- * Calls are made from one host thread.  There is NO CPU fallback: without a
+ * Calls are made from one host thread, and the library holds ONE renderer per
+ * process (a single context: devices, scene, skybox, accumulation, frame
+ * scheduler), as the reference does.  There is NO CPU fallback: without a
  * CUDA device every rendering call fails with RT_ERR_NO_DEVICE.
  */
 #ifndef RT_CUDA_H
@@ -347,6 +349,10 @@ int rt_cuda_debug_set_light_anyhit(int on);
  * side on separate streams and folds them into the frame in pass order with one resolve kernel;
  * 0 = one pass after the other.  Frames, accumulation and ray counts must be identical. */
 int rt_cuda_debug_set_concurrent_sweep(int on);
+/* Test knob: a synchronous call with a HOST frame on one GPU renders the frame as `bands` row bands
+ * (default 4) and copies band k to the host while band k+1 renders; 1 = render, then copy.
+ * Frames must be identical. */
+int rt_cuda_debug_set_sync_bands(int bands);
 /* Unit probe of the longest-tiles-first order: tiles_x*tiles_y tiles ordered by the costs of a map
  * that is 1 << shift times coarser (stable: costly classes first, image order within a class). */
 int rt_cuda_debug_tile_order(const uint32_t *cost, int cost_tiles_x, int cost_tiles_y, int shift,

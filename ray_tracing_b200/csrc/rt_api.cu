@@ -69,6 +69,7 @@ extern "C" const char *rt_cuda_last_error(void) { return g_err; }
 #define RT_MAX_GPUS 16
 #define RT_WORK_SLOTS 8       /* tile counters: launches that may be in flight at once on one GPU */
 #define RT_SWEEP_MAX_COARSE 6 /* passes of a sweep above scale 1 (init_scale <= 64) */
+#define RT_SYNC_BANDS_MAX 8   /* row bands of a synchronous call with a host frame (render_pass) */
 
 /* What the tile costs of a pose are valid for: the same scene seen from the same
  * camera through the same frame, band and interleave -- at any scale. */
@@ -121,6 +122,7 @@ struct DeviceCtx {
 	size_t       stage_bytes[2] = {0, 0};
 	cudaEvent_t  stage_rendered[2] = {nullptr, nullptr}, stage_copied[2] = {nullptr, nullptr};
 	int          stage_next = 0;
+	cudaEvent_t  band_ev[RT_SYNC_BANDS_MAX] = {};     /* banded host read-back (render_pass): band k rendered */
 	/* concurrent sweep (sweep_concurrent): side streams for the coarse passes, their cell buffers */
 	cudaStream_t sweep_stream[RT_SWEEP_MAX_COARSE] = {};
 	cudaEvent_t  sweep_fork = nullptr, sweep_join[RT_SWEEP_MAX_COARSE] = {};
@@ -145,6 +147,7 @@ struct Context {
 	unsigned  scene_epoch = 0;          /* bumped by every scene upload (tile schedules die with the scene) */
 	int       tile_schedule = 1;        /* 0: never reorder tiles (tests / A-B) */
 	int       concurrent_sweep = 1;     /* 0: rt_cuda_render_sweep runs its passes one after the other (tests / A-B) */
+	int       sync_bands = 4;           /* row bands of a synchronous call with a host frame; 1 = render, then copy */
 };
 
 static Context g;
@@ -181,6 +184,7 @@ static void free_device(DeviceCtx &d)
 		if (d.sweep_join[k]) cudaEventDestroy(d.sweep_join[k]);
 	}
 	if (d.sweep_fork) cudaEventDestroy(d.sweep_fork);
+	for (auto &e : d.band_ev) if (e) cudaEventDestroy(e);
 	cudaFree(d.sweep_cells); cudaFree(d.sweep_fine);
 	if (d.stream) cudaStreamDestroy(d.stream);
 	d = DeviceCtx();
@@ -911,6 +915,7 @@ struct LaunchExtra {
 	bool  compact = false;       /* one value per low-res cell instead of the replicated tiles (RtRenderParams::compact) */
 	bool  no_schedule = false;   /* leave the pose's tile schedule alone (launches that overlap one another) */
 	float grid_share = 1.0f;     /* persistent kernels: fraction of the resident CTA slots this launch may take */
+	bool  no_clear = false;      /* the never-written pixels of the CALL's band were cleared by an earlier launch of the call */
 };
 
 static int launch_band(DeviceCtx &d, const RtCamera *cam, const PassPlan &pl, const RtRenderOpts *o,
@@ -961,9 +966,9 @@ static int launch_band(DeviceCtx &d, const RtCamera *cam, const PassPlan &pl, co
 	P.inv_count = inv_count;
 
 	/* pixels the reference's pass never writes hold 0 (clear_uncovered_owned) */
-	int covered_rows_end = std::min(P.lh * pl.scale, r1);
+	int covered_rows_end = std::min(P.lh * pl.scale, pl.row1);    /* of the whole call (r1 == pl.row1 except for the bands of a banded read-back) */
 	bool columns_uncovered = P.column_w * pl.ncols < pl.w;
-	if (!X.compact && (covered_rows_end < r1 || columns_uncovered)) {
+	if (!X.compact && !X.no_clear && (covered_rows_end < pl.row1 || columns_uncovered)) {
 		int rc = clear_uncovered_owned(fb, pl, fb_row_offset, P.il_n, P.il_i, bytes_per_pixel(o->fb_format),
 		                               covered_rows_end, columns_uncovered, stream, launches);
 		if (rc != RT_OK) return rc;
@@ -1158,6 +1163,12 @@ static int render_pass(const RtCamera *cam, void *fb, int w, int h, const RtRend
 		}
 	}
 
+	/* banded read-back: one device, host frame, nothing else overlapping already */
+	int nbands = std::min(g.sync_bands, RT_SYNC_BANDS_MAX);
+	const bool banded = !dev_fb && !pipelined && !piped_peer && ngpu == 1 && o->interleave_count <= 1 && sync_and_copy &&
+	                    nbands > 1 && (pl.persistent || pl.queued) && !pl.wavefront &&
+	                    (size_t) w * (size_t) band_rows >= (size_t) 1 << 20 && band_rows / (pl.scale * RT_TILE_H * 4) >= 2 * nbands;
+
 	/* accumulation weights (main.c:278, 394-396, 476) */
 	float wgt = 1.0f / (float) (pl.scale * pl.scale);
 	float inv = 1.0f;
@@ -1199,11 +1210,46 @@ static int render_pass(const RtCamera *cam, void *fb, int w, int h, const RtRend
 			d.accum_needs_clear = false;
 			launches++;
 		}
+		if (banded) {
+			/* Synchronous call with a HOST frame (what INTEGRATION.md's update_frame() binding makes):
+			 * the frame is rendered as a few row bands, one launch each, and the copy stream sends band
+			 * k to the host while band k+1 renders: 1.9 ms of render + 1.8 ms of PCIe copy per 4K frame
+			 * become ~2.6 ms instead of 3.7.  Bands change nothing in the frame (pixels are independent). */
+			int unit = pl.scale * RT_TILE_H * 4;                  /* whole tiles, 4 tile rows at least */
+			int rows = pl.row1 - pl.row0;
+			int per = ((rows + nbands - 1) / nbands + unit - 1) / unit * unit;
+			/* every launch first, then the copies: a copy into pageable memory blocks the host, and the
+			 * bands behind it must already be queued for the GPU to stay busy meanwhile */
+			int k = 0;
+			for (int r0 = pl.row0; r0 < pl.row1; r0 += per, k++) {
+				int r1 = std::min(r0 + per, pl.row1);
+				if (!d.band_ev[k]) CU(cudaEventCreateWithFlags(&d.band_ev[k], cudaEventDisableTiming));
+				LaunchExtra X;
+				X.no_schedule = true;                               /* one pose, several keys: leave its schedule alone */
+				X.no_clear = k > 0;                                 /* the first launch clears for the whole call */
+				rc = launch_band(d, cam, pl, o, render_to, fb_row_offset, r0, r1, il_n, il_i, st,
+				                 accumulate, wgt, inv, &launches, &X);
+				if (rc != RT_OK) return rc;
+				CU(cudaEventRecord(d.band_ev[k], st));
+			}
+			if (stats) CU(cudaEventRecord(d.ev[1], st));
+			k = 0;
+			for (int r0 = pl.row0; r0 < pl.row1; r0 += per, k++) {
+				int r1 = std::min(r0 + per, pl.row1);
+				CU(cudaStreamWaitEvent(d.copy_stream, d.band_ev[k], 0));
+				if (k == 0 && stats) CU(cudaEventRecord(d.ev[2], d.copy_stream));
+				size_t off = (size_t) (r0 - fb_row_offset) * (size_t) w * bpp;
+				CU(cudaMemcpyAsync((char *) fb + off, (const char *) render_to + off, (size_t) (r1 - r0) * (size_t) w * bpp,
+				                   cudaMemcpyDeviceToHost, d.copy_stream));
+			}
+			if (stats) CU(cudaEventRecord(d.ev[3], d.copy_stream));
+		} else {
 		rc = launch_band(d, cam, pl, o, render_to, fb_row_offset, pl.row0, pl.row1, il_n, il_i, st,
 		                 accumulate, wgt, inv, &launches);
 		if (rc != RT_OK) return rc;
+		}
 		if (remote && ship && !piped_peer && (rc = copy_owned_blocks(target, render_to, pl, fb_row_offset, il_n, il_i, bpp, st)) != RT_OK) return rc;
-		if (stats) CU(cudaEventRecord(d.ev[1], st));
+		if (stats && !banded) CU(cudaEventRecord(d.ev[1], st));
 	}
 
 	if (piped_peer) {
@@ -1259,6 +1305,10 @@ static int render_pass(const RtCamera *cam, void *fb, int w, int h, const RtRend
 	if ((rc = select_device(d0)) != RT_OK) return rc;
 
 	float copy_ms = 0.0f;
+	if (banded) {
+		CU(cudaStreamSynchronize(d0.copy_stream));
+		if (stats) CU(cudaEventElapsedTime(&copy_ms, d0.ev[2], d0.ev[3]));
+	} else
 	if (!dev_fb) {
 		cudaStream_t st = use_user_stream ? (cudaStream_t) o->stream : d0.stream;
 		CU(cudaEventRecord(d0.ev[2], st));
@@ -1980,6 +2030,13 @@ extern "C" int rt_cuda_debug_set_tile_schedule(int on)
 extern "C" int rt_cuda_debug_set_concurrent_sweep(int on)
 {
 	g.concurrent_sweep = on ? 1 : 0;
+	return RT_OK;
+}
+
+/* Test / A-B knob: row bands of a synchronous call with a host frame (1 = render, then copy). */
+extern "C" int rt_cuda_debug_set_sync_bands(int bands)
+{
+	g.sync_bands = bands < 1 ? 1 : (bands > RT_SYNC_BANDS_MAX ? RT_SYNC_BANDS_MAX : bands);
 	return RT_OK;
 }
 

@@ -382,6 +382,36 @@ def test_concurrent_sweep_equals_sequential_passes(renderer, small_sky, builtin_
         renderer.set_concurrent_sweep(True)
 
 
+def test_banded_host_readback_changes_nothing(renderer, small_sky, builtin_objects):
+    """A synchronous call with a host frame renders the frame as row bands and copies band k
+    while band k+1 renders (rt_api.cu: render_pass).  1, 4 and 8 bands must give the same
+    frame, ray count and accumulation: plain and accumulated passes, uncovered columns and
+    rows (W % T, H % scale), the 8-bit format, a caller's row band."""
+    renderer.upload_skybox(small_sky)
+    renderer.upload_scene(builtin_objects[0])
+    W, H = 1600, 901
+    cases = [dict(scale=1), dict(scale=2, num_columns=7, pass_index=3), dict(scale=1, fb_format=RT_FB_U8X4),
+             dict(scale=4, rows=(128, 896)), dict(scale=1, accumulate=1, pass_index=9)]
+    try:
+        got = {}
+        for bands in (1, 4, 8):
+            renderer.set_sync_bands(bands)
+            renderer.accum_reset()
+            out = []
+            for kw in cases:
+                kw = dict(kw)
+                scale = kw.pop("scale")
+                frame, st = renderer.render_frame(Camera(), W, H, scale, **kw)
+                out.append((frame, st["rays"]))
+            got[bands] = out
+        for bands in (4, 8):
+            for (fa, ra), (fb, rb), kw in zip(got[1], got[bands], cases):
+                r0, r1 = kw.get("rows", (0, H))           # rows outside a caller's band are not the call's to define
+                assert ra == rb and np.array_equal(fa[r0:r1].view(np.uint8), fb[r0:r1].view(np.uint8)), (bands, kw)
+    finally:
+        renderer.set_sync_bands(4)
+
+
 def test_update_frame_loop_matches_reference_scheduler(renderer, port, small_sky, builtin_objects):
     """rt_cuda_update_frame / rt_cuda_invalidate_accumulation reproduce the
     workers' schedule (main.c:354, 402-408): init_scale, halving per published
