@@ -1164,7 +1164,9 @@ static int render_pass(const RtCamera *cam, void *fb, int w, int h, const RtRend
 	}
 
 	/* banded read-back: one device, host frame, nothing else overlapping already */
-	int nbands = std::min(g.sync_bands, RT_SYNC_BANDS_MAX);
+	/* a band is worth its launch when it holds ~1.5 M pixels (4K pinned frame: 3.71 / 3.14 / 2.83 / 2.89 / 3.04 ms
+	 * with 1 / 2 / 4 / 6 / 8 bands; 1080p: 1.00 / 0.94 / 1.06 ms with 1 / 2 / 4) */
+	int nbands = (int) std::min<size_t>((size_t) std::min(g.sync_bands, RT_SYNC_BANDS_MAX), ((size_t) w * (size_t) (pl.row1 - pl.row0)) / 1500000);
 	const bool banded = !dev_fb && !pipelined && !piped_peer && ngpu == 1 && o->interleave_count <= 1 && sync_and_copy &&
 	                    nbands > 1 && (pl.persistent || pl.queued) && !pl.wavefront &&
 	                    (size_t) w * (size_t) band_rows >= (size_t) 1 << 20 && band_rows / (pl.scale * RT_TILE_H * 4) >= 2 * nbands;
