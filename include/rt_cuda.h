@@ -350,8 +350,9 @@ int rt_cuda_debug_set_light_anyhit(int on);
  * 0 = one pass after the other.  Frames, accumulation and ray counts must be identical. */
 int rt_cuda_debug_set_concurrent_sweep(int on);
 /* Test knob: a synchronous call with a HOST frame on one GPU renders the frame as `bands` row bands
- * (default 4) and copies band k to the host while band k+1 renders; 1 = render, then copy.
- * Frames must be identical. */
+ * at most (default 4; one band per ~1.5 M pixels) and copies band k to the host while band k+1
+ * renders; 1 = render, then copy; a negative count forces exactly that many bands whatever the
+ * frame size.  Frames must be identical. */
 int rt_cuda_debug_set_sync_bands(int bands);
 /* Unit probe of the longest-tiles-first order: tiles_x*tiles_y tiles ordered by the costs of a map
  * that is 1 << shift times coarser (stable: costly classes first, image order within a class). */

@@ -147,7 +147,8 @@ struct Context {
 	unsigned  scene_epoch = 0;          /* bumped by every scene upload (tile schedules die with the scene) */
 	int       tile_schedule = 1;        /* 0: never reorder tiles (tests / A-B) */
 	int       concurrent_sweep = 1;     /* 0: rt_cuda_render_sweep runs its passes one after the other (tests / A-B) */
-	int       sync_bands = 4;           /* row bands of a synchronous call with a host frame; 1 = render, then copy */
+	int       sync_bands = 4;           /* most row bands of a synchronous call with a host frame; 1 = render, then copy */
+	bool      sync_bands_forced = false;/* tests: exactly that many, whatever the frame size */
 };
 
 static Context g;
@@ -1167,9 +1168,10 @@ static int render_pass(const RtCamera *cam, void *fb, int w, int h, const RtRend
 	/* a band is worth its launch when it holds ~1.5 M pixels (4K pinned frame: 3.71 / 3.14 / 2.83 / 2.89 / 3.04 ms
 	 * with 1 / 2 / 4 / 6 / 8 bands; 1080p: 1.00 / 0.94 / 1.06 ms with 1 / 2 / 4) */
 	int nbands = (int) std::min<size_t>((size_t) std::min(g.sync_bands, RT_SYNC_BANDS_MAX), ((size_t) w * (size_t) (pl.row1 - pl.row0)) / 1500000);
+	if (g.sync_bands_forced) nbands = std::min(g.sync_bands, RT_SYNC_BANDS_MAX);
 	const bool banded = !dev_fb && !pipelined && !piped_peer && ngpu == 1 && o->interleave_count <= 1 && sync_and_copy &&
 	                    nbands > 1 && (pl.persistent || pl.queued) && !pl.wavefront &&
-	                    (size_t) w * (size_t) band_rows >= (size_t) 1 << 20 && band_rows / (pl.scale * RT_TILE_H * 4) >= 2 * nbands;
+	                    band_rows / (pl.scale * RT_TILE_H * 4) >= 2 * nbands;
 
 	/* accumulation weights (main.c:278, 394-396, 476) */
 	float wgt = 1.0f / (float) (pl.scale * pl.scale);
@@ -2038,6 +2040,8 @@ extern "C" int rt_cuda_debug_set_concurrent_sweep(int on)
 /* Test / A-B knob: row bands of a synchronous call with a host frame (1 = render, then copy). */
 extern "C" int rt_cuda_debug_set_sync_bands(int bands)
 {
+	g.sync_bands_forced = bands < 0;            /* negative: exactly -bands bands whatever the frame size (tests) */
+	if (bands < 0) bands = -bands;
 	g.sync_bands = bands < 1 ? 1 : (bands > RT_SYNC_BANDS_MAX ? RT_SYNC_BANDS_MAX : bands);
 	return RT_OK;
 }

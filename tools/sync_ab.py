@@ -25,7 +25,7 @@ def main():
         pageable = np.zeros((H, W, 3), np.float32)
         out = {"size": f"{W}x{H}"}
         for bands in (1, 2, 3, 4, 6, 8):
-            r.set_sync_bands(bands)
+            r.set_sync_bands(-bands if bands > 1 else 1)
             for name, ptr in (("pinned", pinned.data_ptr()), ("pageable", pageable.ctypes.data)):
                 for k in range(3):
                     r.render_into(cam, ptr, W, H, host=True, pass_index=k)
