@@ -1011,7 +1011,7 @@ static int launch_band(DeviceCtx &d, const RtCamera *cam, const PassPlan &pl, co
 			grid = (int) std::min<unsigned>(slots, blocks_needed);
 		}
 		bool sched = false;
-		if (pl.queued && !X.no_schedule) {
+		if ((pl.queued || (pl.lbvh && pl.persistent && !pl.wavefront)) && !X.no_schedule) {     /* the kernels that read P.tile_order */
 			TileKey key;
 			memset(&key, 0, sizeof(key));
 			key.w = pl.w; key.h = pl.h; key.ncols = pl.ncols; key.r0 = r0; key.r1 = r1;

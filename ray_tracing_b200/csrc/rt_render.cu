@@ -420,17 +420,23 @@ render_persistent_kernel(const __grid_constant__ RtRenderParams P)
 	bool owns = false;          /* lane holds a pixel whose path is running or just ended */
 	unsigned rays = 0;
 	unsigned batch_next = 0, batch_end = 0;   /* warp-uniform: tile-ordered pixel indices */
+	unsigned batch_delta = 0;                 /* warp-uniform: (tile handed out << 5) - batch base, when P.tile_order deals the tiles */
 	bool exhausted = false;                   /* warp-uniform */
 
 	for (;;) {
 		unsigned idle = __ballot_sync(full, p.mode == MODE_IDLE);
 		if (idle) {
 			path_unpark<PARK>(p, S);
+			const bool ended = p.mode == MODE_IDLE && owns;
+			/* longest tiles first (rt_api.cu: tile_schedule): what this pixel's path cost, for the pose's next pass */
+			if (ended && P.tile_cost && p.bounce) atomicMax(P.tile_cost + ((unsigned) c.tw >> 12), (unsigned) p.bounce);
+			Cell out = c;
+			out.tw = c.tw & 4095;                  /* the tile index rides in the upper bits */
 			if (P.store_scale >= 4) {       /* warp-uniform */
-				store_cells_warp(P, p.mode == MODE_IDLE && owns, c, path_final(p));
+				store_cells_warp(P, ended, out, path_final(p));
 				if (p.mode == MODE_IDLE) owns = false;
-			} else if (p.mode == MODE_IDLE && owns) {
-				store_cell(P, c, path_final(p));
+			} else if (ended) {
+				store_cell(P, out, path_final(p));
 				owns = false;
 			}
 			if (batch_next == batch_end && !exhausted) {
@@ -438,26 +444,35 @@ render_persistent_kernel(const __grid_constant__ RtRenderParams P)
 				 * single tiles at the end.  A path is up to 40 rays long and a warp
 				 * step takes microseconds, so a warp that claims 8 tiles of a
 				 * mirror-heavy region late in the launch would otherwise BE the
-				 * launch's tail (measured: 0.75 ms floor on a 3.2 ms frame). */
-				unsigned base = 0, claim = 0;
+				 * launch's tail (measured: 0.75 ms floor on a 3.2 ms frame).  With a
+				 * longest-first order every claim is ONE tile (see render_queued_kernel). */
+				unsigned base = 0, claim = 32u;
 				if (lane == 0) {
-					unsigned seen = *(volatile unsigned *) P.work_counter;
-					unsigned left = seen < total ? (total - seen) >> 5 : 0;
-					unsigned warps = gridDim.x * (RT_BLOCK_THREADS / 32);
-					claim = min(max(left / (4u * warps), 1u), (unsigned) RT_WARP_BATCH) * 32u;
+					if (!P.tile_order) {
+						unsigned seen = *(volatile unsigned *) P.work_counter;
+						unsigned left = seen < total ? (total - seen) >> 5 : 0;
+						unsigned warps = gridDim.x * (RT_BLOCK_THREADS / 32);
+						claim = min(max(left / (4u * warps), 1u), (unsigned) RT_WARP_BATCH) * 32u;
+					}
 					base = atomicAdd(P.work_counter, claim);
 				}
 				base = __shfl_sync(full, base, 0);
 				claim = __shfl_sync(full, claim, 0);
 				if (base >= total) exhausted = true;
-				else { batch_next = base; batch_end = min(base + claim, total); }
+				else {
+					batch_next = base;
+					batch_end = min(base + claim, total);
+					batch_delta = P.tile_order ? (__ldg(P.tile_order + (base >> 5)) << 5) - base : 0u;
+				}
 			}
 			/* hand the idle lanes the next pixels of the warp's batch */
 			unsigned avail = batch_end - batch_next;
 			unsigned rank = __popc(idle & ((1u << lane) - 1u));
 			int cx, cy;
-			if (p.mode == MODE_IDLE && rank < avail && cell_of(P, batch_next + rank, cx, cy)) {
+			const unsigned idx = batch_next + rank + batch_delta;
+			if (p.mode == MODE_IDLE && rank < avail && cell_of(P, idx, cx, cy)) {
 				c = cell_geometry(P, cx, cy);
+				c.tw |= (int) ((idx >> 5) << 12);
 				path_begin(p, P.cam, c.u, c.v, P.pass_mix);
 				owns = true;
 			}

@@ -624,6 +624,39 @@ def test_tile_schedule_changes_nothing(renderer, port, small_sky, builtin_object
         renderer.set_tile_schedule(True)
 
 
+def test_tile_schedule_of_the_lbvh_kernel_changes_nothing(renderer, small_sky):
+    """The persistent kernel over the LBVH records tile costs and hands tiles out longest-first like
+    the queued kernel (a 1/8 share of BASELINE config 5 spent a quarter of its launch in the tail).
+    Every launch of a pose -- image order, recording, reordered, interleaved shares -- must equal
+    the unscheduled frame (which test_large_scene_lbvh_vs_oracle and the config-5 tiles pin)."""
+    import torch
+
+    W, H = 640, 360
+    objs = host.parse_scene_string_large(scenes.synthetic_spheres_text(3000, seed=5))
+    renderer.upload_skybox(small_sky)
+    renderer.upload_scene(objs)
+    frame = torch.empty((H, W, 3), dtype=torch.float32, device="cuda")
+    try:
+        renderer.set_tile_schedule(False)
+        frame.fill_(-1.0)
+        st0 = renderer.render_into(Camera(), frame.data_ptr(), W, H, stats=True)
+        want = frame.cpu().numpy().copy()
+        assert want.min() >= 0.0
+        for mode in (True, 2):
+            renderer.set_tile_schedule(mode)
+            for launch in range(4):
+                frame.fill_(-1.0)
+                st = renderer.render_into(Camera(), frame.data_ptr(), W, H, stats=True)
+                assert np.array_equal(bits(frame.cpu().numpy()), bits(want)) and st["rays"] == st0["rays"], (mode, launch)
+            for rep in range(3):
+                frame.fill_(-1.0)
+                for rank in range(2):
+                    renderer.render_into(Camera(), frame.data_ptr(), W, H, stats=True, interleave_count=2, interleave_index=rank)
+                assert np.array_equal(bits(frame.cpu().numpy()), bits(want)), (mode, rep)
+    finally:
+        renderer.set_tile_schedule(True)
+
+
 def test_gl_presenter_fails_loudly_without_a_gl_context(renderer, small_sky, builtin_objects):
     """SURVEY N3: the CUDA-OpenGL presenter cannot be exercised on a headless box;
     what can be is that it reports the missing GL context / buffer as an error
