@@ -338,6 +338,10 @@ class GpuBench:
         self.kernel = {"auto": host.RT_KERNEL_AUTO, "pixel": host.RT_KERNEL_PIXEL, "persistent": host.RT_KERNEL_PERSISTENT,
                        "wavefront": host.RT_KERNEL_WAVEFRONT, "queued": host.RT_KERNEL_QUEUED}[args.kernel]
         self.render_stream = torch.cuda.current_stream()
+        # frames in flight: consecutive frames are issued on these streams round robin (each into its own
+        # frame buffer), so that the tail of frame k -- a few long paths on a nearly idle GPU -- runs under
+        # the head of frame k+1.  render_streams[0] is the timing stream.
+        self.render_streams = [self.render_stream] + [torch.cuda.Stream() for _ in range(max(args.streams, 1) - 1)]
         self.consumer_stream = torch.cuda.Stream(priority=-1)
         self.scene_loaded = None
         self.shared = {}        # frame bytes -> (ptr, seq)
@@ -407,16 +411,19 @@ class GpuBench:
         common = dict(variant=self.variant, kernel=self.kernel)
         sweep = cfg["kind"] == "sweep"
         bpp = 12
+        # a sweep owns the library's accumulation and cell buffers: one stream; plain frames: all of them
+        nst = 1 if sweep else len(self.render_streams)
+        streams = [s_.cuda_stream for s_ in self.render_streams[:nst]]
         if self.world == 1:
-            frame = torch.empty((H, W, 3), dtype=torch.float32, device=self.dev)
-            rs = self.render_stream.cuda_stream
+            frames = [torch.empty((H, W, 3), dtype=torch.float32, device=self.dev) for _ in range(nst)]
+            frame = frames[0]
 
             def issue(k, stats=False):
                 # pass k of the pose: the reference's accumulation draws fresh samples every pass (main.c:354-403)
                 if sweep:
-                    _, st = r.render_sweep(cam, W, H, cfg["init_scale"], 5 * k, ptr=frame.data_ptr(), stats=stats, stream=rs, **common)
+                    _, st = r.render_sweep(cam, W, H, cfg["init_scale"], 5 * k, ptr=frame.data_ptr(), stats=stats, stream=streams[0], **common)
                     return st
-                return r.render_into(cam, frame.data_ptr(), W, H, stats=stats, stream=rs, scale=1, pass_index=k, **common)
+                return r.render_into(cam, frames[k % nst].data_ptr(), W, H, stats=stats, stream=streams[k % nst], scale=1, pass_index=k, **common)
 
             st = issue(0, stats=True)
             rays = st["rays"]
@@ -467,7 +474,7 @@ class GpuBench:
             if sweep:
                 r.render_sweep(cam, W, H, cfg["init_scale"], 5 * k, ptr=ptr, stats=False, stream=rs, frame_seq=seq, frame_ack=1, **il, **common)
             else:
-                r.render_into(cam, ptr, W, H, stream=rs, scale=1, pass_index=k, frame_seq=seq, frame_ack=1, **il, **common)
+                r.render_into(cam, ptr, W, H, stream=streams[seq % nst], scale=1, pass_index=k, frame_seq=seq, frame_ack=1, **il, **common)
             if self.rank == 0:
                 # the consumer: frame seq is whole once every rank's blocks have landed; hand it back at once
                 r.shared_frame_wait(ptr, self.world, seq, stream=cs)
@@ -507,8 +514,12 @@ class GpuBench:
         rays0 = self.r.ray_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(self.render_stream)
+        for s_ in self.render_streams[1:]:
+            s_.wait_event(e0)
         for _ in range(steps):
             step()
+        for s_ in self.render_streams[1:]:
+            self.render_stream.wait_stream(s_)
         finish()
         e1.record(self.render_stream)
         self.r.synchronize()
@@ -723,6 +734,7 @@ def main_gpu(args):
                 "framebuffer": "Vector3 f32x3 (reference frame format), bottom row first",
                 "l2": "no explicit flush: every step reads the 96 MiB RGBA8 skybox at random and writes a %.1f MB frame (working set > 126 MB L2 at 4K)" % (W * H * 12 / 1e6),
                 "rays_per_step": rays_per_step, "pixels_per_step": W * H,
+                "frames_in_flight": "consecutive frames are issued on %d CUDA streams round robin, each into its own frame buffer (N > 1: its own staging frame), so the tail of frame k overlaps the head of frame k+1; every frame is complete and composited before the timed region ends (--streams 1: one after the other)" % len(b.render_streams),
                 "schedule": "every step renders the same pose, as the reference's progressive accumulation does (main.c:354-403); from the third launch of a pose the queued kernel hands out its 8x4 tiles longest-first, by the per-tile bounce counts the second launch recorded (warm-up). Scheduling only: frames are bit-identical. `unscheduled` = the same loop with tiles in image order",
             },
             "frames_per_s": 1e3 / per_step_ms,
@@ -881,6 +893,7 @@ def main():
     ap.add_argument("--config", default="3", choices=sorted(CONFIGS))
     ap.add_argument("--variant", default="exact", choices=["exact", "fast"])
     ap.add_argument("--kernel", default="auto", choices=["auto", "pixel", "persistent", "wavefront", "queued"])
+    ap.add_argument("--streams", type=int, default=3, help="frames in flight: consecutive frames are issued on this many streams round robin (1 = one after the other)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="config 3 only: skip the short measurements of the other configs")
     args = ap.parse_args()

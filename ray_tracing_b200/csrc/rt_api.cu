@@ -92,6 +92,15 @@ struct TileSched {
 	cudaEvent_t   fence = nullptr;                  /* after the last launch that touched these buffers */
 	unsigned int *hist = nullptr;                   /* scratch of launch_tile_order() */
 	cudaStream_t  last_stream = nullptr;
+	/* Launches of a pose on DIFFERENT streams may overlap (the tail of one frame under the head of the
+	 * next: a 1/8 share of a 4K frame takes 0.27 ms alone and 0.19 ms per frame on three streams) as
+	 * long as they only READ the order.  A launch that WRITES (records costs, builds an order) waits
+	 * for the last use on every other stream; a reader waits for the last writer. */
+	struct Use { cudaStream_t st = nullptr; cudaEvent_t ev = nullptr; } uses[4];
+	int           nuses = 0;
+	cudaEvent_t   write_fence = nullptr;
+	cudaStream_t  write_stream = nullptr;
+	bool          launch_writes = false;            /* the launch being issued */
 };
 
 struct DeviceCtx {
@@ -171,6 +180,8 @@ static void free_device(DeviceCtx &d)
 	for (int k = 0; k < 2; k++) { cudaFree(d.sched.cost[k]); cudaFree(d.sched.order[k]); }
 	cudaFree(d.sched.hist);
 	if (d.sched.fence) cudaEventDestroy(d.sched.fence);
+	if (d.sched.write_fence) cudaEventDestroy(d.sched.write_fence);
+	for (auto &u : d.sched.uses) if (u.ev) cudaEventDestroy(u.ev);
 	d.sched = TileSched();
 	if (d.host_rays) cudaFreeHost(d.host_rays);
 	for (auto &e : d.ev) if (e) cudaEventDestroy(e);
@@ -858,8 +869,21 @@ static bool tile_schedule(DeviceCtx &d, const TileKey &key, int scale, int tiles
 		S.cost_cur = S.order_cur = -1;      /* a new pose: nothing is known about it */
 	}
 	if (!S.fence && cudaEventCreateWithFlags(&S.fence, cudaEventDisableTiming) != cudaSuccess) return false;
-	/* the buffers are used in stream order; a caller that switches streams waits for the last user */
-	if (S.last_stream != stream && S.last_stream) cudaStreamWaitEvent(stream, S.fence, 0);
+	if (!S.write_fence && cudaEventCreateWithFlags(&S.write_fence, cudaEventDisableTiming) != cudaSuccess) return false;
+	/* what this launch will do (decided before anything is queued, so that it can wait first) */
+	bool keeps = false, builds = false, records = false;
+	if (tiles >= 2048) {
+		const bool exact_costs = S.cost_cur >= 0 && S.cost_scale == scale;
+		keeps = S.order_cur >= 0 && S.order_scale == scale && S.order_tiles == tiles && (S.order_from_scale == scale || !exact_costs);
+		builds = !keeps && S.cost_cur >= 0 && S.cost_scale >= scale && S.cost_scale % scale == 0 && (g.tile_schedule == 2 || S.cost_scale == scale);
+	}
+	records = tiles >= 64 && (S.cost_cur < 0 || S.cost_scale > scale);
+	S.launch_writes = builds || records;
+	if (S.launch_writes) {
+		for (int i = 0; i < S.nuses; i++)
+			if (S.uses[i].st != stream) cudaStreamWaitEvent(stream, S.uses[i].ev, 0);
+	} else if (S.write_stream && S.write_stream != stream)
+		cudaStreamWaitEvent(stream, S.write_fence, 0);
 	S.last_stream = stream;
 	bool touched = false;
 
@@ -909,6 +933,23 @@ static void tile_schedule_done(DeviceCtx &d, const RtRenderParams &P, int scale,
 		S.cost_scale = scale; S.cost_tiles_x = tiles_x; S.cost_tiles_y = tiles_y;
 	}
 	cudaEventRecord(S.fence, stream);
+	int slot = -1;
+	for (int i = 0; i < S.nuses; i++) if (S.uses[i].st == stream) slot = i;
+	if (slot < 0 && S.nuses < 4 && cudaEventCreateWithFlags(&S.uses[S.nuses].ev, cudaEventDisableTiming) == cudaSuccess)
+		slot = S.nuses++;
+	if (slot < 0) {
+		/* more streams than slots: take over the slot of a stream whose last use is over (waiting for
+		 * one if need be: callers that rotate through many streams are rare) */
+		for (int i = 0; i < S.nuses && slot < 0; i++) if (cudaEventQuery(S.uses[i].ev) == cudaSuccess) slot = i;
+		if (slot < 0) { slot = 0; cudaEventSynchronize(S.uses[0].ev); }
+		cudaGetLastError();
+	}
+	S.uses[slot].st = stream;
+	cudaEventRecord(S.uses[slot].ev, stream);
+	if (S.launch_writes) {
+		cudaEventRecord(S.write_fence, stream);
+		S.write_stream = stream;
+	}
 }
 
 /* Launch one pass for one device over output rows [r0, r1) (scale aligned). */

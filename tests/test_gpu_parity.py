@@ -624,6 +624,36 @@ def test_tile_schedule_changes_nothing(renderer, port, small_sky, builtin_object
         renderer.set_tile_schedule(True)
 
 
+def test_frames_in_flight_on_several_streams(renderer, small_sky, builtin_objects):
+    """Frames of one pose issued on different streams may overlap on the GPU (bench.py keeps three in
+    flight).  The pose's tile schedule is shared state: launches that record costs or build an order
+    wait for every other stream, launches that only read it wait for the last writer (rt_api.cu:
+    tile_schedule).  Every frame must equal the frame rendered alone, from the very first launches
+    of the pose (recording, building) on, for both kernels that use the schedule."""
+    import torch
+
+    W, H = 640, 360
+    renderer.upload_skybox(small_sky)
+    for objs, kw in ((builtin_objects[0], {}), (host.parse_scene_string_large(scenes.synthetic_spheres_text(3000, seed=5)), {})):
+        renderer.upload_scene(objs)
+        want = {}
+        ref = torch.empty((H, W, 3), dtype=torch.float32, device="cuda")
+        renderer.set_tile_schedule(False)
+        for k in range(4):
+            renderer.render_into(Camera(), ref.data_ptr(), W, H, stats=True, pass_index=k, **kw)
+            want[k] = ref.cpu().numpy().copy()
+        renderer.set_tile_schedule(True)
+        streams = [torch.cuda.Stream() for _ in range(3)]
+        bufs = [torch.full((H, W, 3), -1.0, dtype=torch.float32, device="cuda") for _ in range(12)]
+        for cam in (Camera(), Camera((4.0, 4.5, 6.0), (-1.0, -0.8, -1.2), (0, 1, 0), 30.0), Camera()):
+            for i in range(12):
+                renderer.render_into(cam, bufs[i].data_ptr(), W, H, stream=streams[i % 3].cuda_stream, pass_index=i % 4, **kw)
+            torch.cuda.synchronize()
+            if cam.pos == Camera().pos:
+                for i in range(12):
+                    assert np.array_equal(bits(bufs[i].cpu().numpy()), bits(want[i % 4])), i
+
+
 def test_tile_schedule_of_the_lbvh_kernel_changes_nothing(renderer, small_sky):
     """The persistent kernel over the LBVH records tile costs and hands tiles out longest-first like
     the queued kernel (a 1/8 share of BASELINE config 5 spent a quarter of its launch in the tail).
