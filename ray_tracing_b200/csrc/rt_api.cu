@@ -681,6 +681,27 @@ static int copy_owned_blocks(void *dst, const void *src, const PassPlan &pl, int
 	return RT_OK;
 }
 
+/* Pipelined composite, second half: staging frame `slot` of this rank holds its blocks of frame
+ * o.frame_seq (rendered on `st`); the copy stream ships them into the shared frame `fb` and raises
+ * the rank's arrived flag.  Returns after queueing. */
+static int ship_piped_peer(DeviceCtx &d0, const PassPlan &pl, const RtRenderOpts &o, void *fb, int fb_row_offset, int slot,
+                           int il_n, int il_i, size_t bpp, cudaStream_t st)
+{
+	int rc;
+	SharedHeader *hdr = header_of(fb);
+	CU(cudaEventRecord(d0.stage_rendered[slot], st));
+	CU(cudaStreamWaitEvent(d0.copy_stream, d0.stage_rendered[slot], 0));
+	if (o.frame_ack) {
+		flag_ack_kernel<<<1, 1, 0, d0.copy_stream>>>(hdr, o.frame_seq);
+		CU(cudaGetLastError());
+	}
+	if ((rc = copy_owned_blocks(fb, d0.stage[slot], pl, fb_row_offset, il_n, il_i, bpp, d0.copy_stream)) != RT_OK) return rc;
+	flag_arrive_kernel<<<1, 1, 0, d0.copy_stream>>>(hdr, il_i, o.frame_seq);
+	CU(cudaGetLastError());
+	CU(cudaEventRecord(d0.stage_copied[slot], d0.copy_stream));
+	return RT_OK;
+}
+
 /* Pixels the reference's pass never writes (main.c:285-290: rows >= lh*scale;
  * main.c:363: columns >= T*column_w) hold 0.  Every GPU clears them in ITS
  * render target and only inside the row blocks it owns (copy_owned_blocks ships
@@ -1299,18 +1320,7 @@ static int render_pass(const RtCamera *cam, void *fb, int w, int h, const RtRend
 
 	if (piped_peer) {
 		cudaStream_t st = use_user_stream ? (cudaStream_t) o->stream : d0.stream;
-		SharedHeader *hdr = header_of(fb);
-		CU(cudaEventRecord(d0.stage_rendered[slot], st));
-		CU(cudaStreamWaitEvent(d0.copy_stream, d0.stage_rendered[slot], 0));
-		if (o->frame_ack) {
-			flag_ack_kernel<<<1, 1, 0, d0.copy_stream>>>(hdr, o->frame_seq);
-			CU(cudaGetLastError());
-		}
-		if ((rc = copy_owned_blocks(fb, d0.stage[slot], pl, fb_row_offset, il_n, il_base, bpp, d0.copy_stream)) != RT_OK) return rc;
-		flag_arrive_kernel<<<1, 1, 0, d0.copy_stream>>>(hdr, il_base, o->frame_seq);
-		CU(cudaGetLastError());
-		CU(cudaEventRecord(d0.stage_copied[slot], d0.copy_stream));
-		return RT_OK;
+		return ship_piped_peer(d0, pl, *o, fb, fb_row_offset, slot, il_n, il_base, bpp, st);
 	}
 	if (pipelined) {
 		cudaStream_t st = use_user_stream ? (cudaStream_t) o->stream : d0.stream;
@@ -1445,6 +1455,7 @@ struct SweepResolve {
 	void  *fb;
 	int    fb_format;
 	int    W, H, column_w, covered_w;
+	int    il_n, il_i;        /* this rank owns the blocks b of RT_INTERLEAVE_ROWS output rows with b % il_n == il_i */
 	float  inv_count;
 };
 
@@ -1452,6 +1463,7 @@ __global__ void __launch_bounds__(256) sweep_resolve_kernel(const __grid_constan
 {
 	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
 	if (x >= R.W) return;
+	if (R.il_n > 1 && (y / RT_INTERLEAVE_ROWS) % R.il_n != R.il_i) return;     /* another rank's rows */
 	const size_t p = (size_t) y * R.W + x;
 	float ax = 0.0f, ay = 0.0f, az = 0.0f;
 	if (x < R.covered_w) {            /* main.c:363: columns beyond T * column_w are never rendered */
@@ -1488,7 +1500,12 @@ __global__ void __launch_bounds__(256) sweep_resolve_kernel(const __grid_constan
 static bool sweep_can_run_concurrently(int w, int h, int init_scale, const RtRenderOpts &o)
 {
 	if (!g.concurrent_sweep || g.ngpu != 1 || init_scale < 2 || init_scale > 64) return false;
-	if (o.interleave_count > 1 || o.remote_fb || o.pipeline || o.frame_seq || o.band_only_fb) return false;
+	if (o.pipeline || o.band_only_fb) return false;
+	/* ranks of a one-process-per-GPU run: only in the pipelined composite (the sweep's frame goes to a
+	 * staging frame and is shipped by the copy stream); every other split takes the passes in turn */
+	const bool rank_mode = o.interleave_count > 1;
+	if (rank_mode && !(o.remote_fb && o.frame_seq != 0 && init_scale <= RT_INTERLEAVE_ROWS)) return false;
+	if (!rank_mode && (o.remote_fb || o.frame_seq)) return false;
 	if (!((o.row_begin == 0 && o.row_end == 0) || (o.row_begin == 0 && o.row_end == h))) return false;
 	if (o.kernel == RT_KERNEL_WAVEFRONT || o.kernel == RT_KERNEL_PIXEL) return false;
 	(void) w;
@@ -1517,6 +1534,10 @@ static int sweep_concurrent(const RtCamera *cam, void *fb, int w, int h, int ini
 	cudaStream_t main_st = o.stream ? (cudaStream_t) o.stream : d.stream;
 	const size_t bpp = bytes_per_pixel(o.fb_format);
 	int launches = 0;
+	const bool piped = o.interleave_count > 1;             /* a rank of the pipelined composite (sweep_can_run_concurrently) */
+	const int il_n = piped ? o.interleave_count : 1, il_i = piped ? o.interleave_index : 0;
+	if (piped && (stats || !dev_fb)) return fail(RT_ERR_ARG, "a pipelined composite (frame_seq) takes a device frame and no statistics");
+	if (piped && (il_i < 0 || il_i >= il_n || il_n > RT_MAX_GPUS)) return fail(RT_ERR_ARG, "interleave_index out of range");
 
 	/* the passes */
 	int scales[RT_SWEEP_MAX_COARSE + 1], npass = 0;
@@ -1548,6 +1569,21 @@ static int sweep_concurrent(const RtCamera *cam, void *fb, int w, int h, int ini
 	if ((rc = ensure_accum(d, w, h, 0, h, &fresh)) != RT_OK) return rc;
 	d.accum_needs_clear = false;                    /* the resolve writes every pixel */
 	void *target = fb;
+	int slot = 0;
+	if (piped) {
+		/* the resolved frame goes to one of the two staging frames; the copy stream ships it (render_pass) */
+		size_t need = (size_t) w * h * bpp;
+		slot = d.stage_next;
+		d.stage_next ^= 1;
+		if (d.stage_bytes[slot] < need) {
+			CU(cudaFree(d.stage[slot]));
+			d.stage[slot] = nullptr; d.stage_bytes[slot] = 0;
+			CU(cudaMalloc(&d.stage[slot], need));
+			d.stage_bytes[slot] = need;
+		}
+		CU(cudaStreamWaitEvent(main_st, d.stage_copied[slot], 0));
+		target = d.stage[slot];
+	} else
 	if (!dev_fb) {
 		size_t need = (size_t) w * h * bpp;
 		if (d.fb_bytes < need) {
@@ -1606,7 +1642,7 @@ static int sweep_concurrent(const RtCamera *cam, void *fb, int w, int h, int ini
 		cudaStream_t st = fine ? main_st : d.sweep_stream[k];
 		void *out = fine ? (void *) d.sweep_fine : (void *) (d.sweep_cells + cell_off[k]);
 		if (!fine) CU(cudaStreamWaitEvent(st, d.sweep_fork, 0));
-		rc = launch_band(d, cam, pl, &oo, out, 0, 0, h, 1, 0, st, false, wgt, 1.0f, &launches, &X);
+		rc = launch_band(d, cam, pl, &oo, out, 0, 0, h, il_n, il_i, st, false, wgt, 1.0f, &launches, &X);
 		if (rc != RT_OK) return rc;
 		if (!fine) {
 			CU(cudaEventRecord(d.sweep_join[k], st));
@@ -1622,12 +1658,17 @@ static int sweep_concurrent(const RtCamera *cam, void *fb, int w, int h, int ini
 	R.fb = target;
 	R.fb_format = o.fb_format;
 	R.W = w; R.H = h; R.column_w = column_w; R.covered_w = column_w * ncols;
+	R.il_n = il_n; R.il_i = il_i;
 	g.accum_count = count;
 	R.inv_count = 1.0f / count;                                /* main.c:476 */
 	sweep_resolve_kernel<<<dim3((unsigned) ((w + 255) / 256), (unsigned) h), 256, 0, main_st>>>(R);
 	CU(cudaGetLastError());
 	launches++;
 	if (stats) CU(cudaEventRecord(d.ev[1], main_st));
+	if (piped) {
+		pl.scale = 1;
+		return ship_piped_peer(d, pl, o, fb, 0, slot, il_n, il_i, bpp, main_st);
+	}
 
 	/* with a caller stream, a device frame and no statistics the whole sweep is stream-ordered */
 	if (dev_fb && o.stream && !stats) return RT_OK;

@@ -69,16 +69,16 @@ def test_all_ranks_played_by_one_process(small_sky, builtin_objects):
                     r.copy_async(ptr, poison.ctypes.data, poison.nbytes)
                     r.synchronize()
                     for seq in (1, 2, 3):
-                        if sweep:
-                            # accumulation is per context: one process can only play ONE rank of a sweep at a time
-                            break
                         for rank in range(world):
-                            r.render_into(cam, ptr, W, H, scale=scale, num_columns=ncols, interleave_count=world, interleave_index=rank,
-                                          remote_fb=1, frame_seq=seq, frame_ack=1)
+                            il = dict(interleave_count=world, interleave_index=rank, remote_fb=1, frame_seq=seq, frame_ack=1)
+                            if sweep:
+                                # a rank's sweep in the pipelined composite is self-contained (rt_api.cu: sweep_concurrent
+                                # resolves the rank's own rows from its own cell buffers), so one process can play them in turn
+                                r.render_sweep(cam, W, H, sweep, 0, ptr=ptr, stats=False, **il)
+                            else:
+                                r.render_into(cam, ptr, W, H, scale=scale, num_columns=ncols, **il)
                         r.shared_frame_wait(ptr, world, seq)
                         r.shared_frame_release(ptr, seq)
-                    if sweep:
-                        continue
                     r.synchronize()
                     assert r.shared_frame_error(ptr) == 0
                     got = np.empty((H, W, 3), np.float32)
