@@ -798,6 +798,15 @@ def measure_e2e(b, cfg, rays_per_step, args):
         host_addr = shared_host.ctypes.data
         err = torch.cuda.cudart().cudaHostRegister(host_addr, shared_host.nbytes, 0)
         assert int(err) == 0, f"cudaHostRegister failed: {err}"
+        # the same for the 8-bit frame format (a third of the bytes into host memory)
+        shm8_path = shm_path + "_u8"
+        if rank == 0:
+            np.lib.format.open_memmap(shm8_path, mode="w+", dtype=np.uint8, shape=(H, W, 4)).flush()
+        b.dist.barrier()
+        shared_host8 = np.load(shm8_path, mmap_mode="r+")
+        host_addr8 = shared_host8.ctypes.data
+        err = torch.cuda.cudart().cudaHostRegister(host_addr8, shared_host8.nbytes, 0)
+        assert int(err) == 0, f"cudaHostRegister failed: {err}"
 
     def step(i, pipeline, fmt):
         bpp = 4 if fmt == host.RT_FB_U8X4 else 12
@@ -815,7 +824,8 @@ def measure_e2e(b, cfg, rays_per_step, args):
             # pipeline=1: the call returns once the copy is queued; frame i+1 renders while frame i drains
             r.render_into(b.cam, host_frames[bpp][i & 1].data_ptr(), W, H, host=True, pipeline=int(pipeline), scale=1, pass_index=0, fb_format=fmt, **opts)
         else:
-            r.render_into(b.cam, host_addr, W, H, host=True, pipeline=int(pipeline), scale=1, pass_index=0, interleave_count=world, interleave_index=rank, **opts)
+            r.render_into(b.cam, host_addr8 if bpp == 4 else host_addr, W, H, host=True, pipeline=int(pipeline), scale=1, pass_index=0, fb_format=fmt,
+                          interleave_count=world, interleave_index=rank, **opts)
             if not pipeline:
                 b.dist.barrier()      # the frame is whole once every rank's copy has landed
 
@@ -834,7 +844,7 @@ def measure_e2e(b, cfg, rays_per_step, args):
     n = max(3, min(args.steps, 20))
     sync_s = run(n, False)
     pipe_s = run(n, True) if not sweep else sync_s
-    u8_s = run(n, True, host.RT_FB_U8X4) if world == 1 else None
+    u8_s = run(n, True, host.RT_FB_U8X4) if (world == 1 or not sweep) else None
     # the frame the host ends up with, through the synchronous call
     step(0, False, host.RT_FB_F32X3)
     r.synchronize()
@@ -845,13 +855,15 @@ def measure_e2e(b, cfg, rays_per_step, args):
     if world > 1:
         b.dist.barrier()
         torch.cuda.cudart().cudaHostUnregister(host_addr)
-        del shared_host
+        torch.cuda.cudart().cudaHostUnregister(host_addr8)
+        del shared_host, shared_host8
         b.dist.barrier()
         if rank == 0:
-            try:
-                os.unlink(shm_path)
-            except OSError:
-                pass
+            for path in (shm_path, shm8_path):
+                try:
+                    os.unlink(path)
+                except OSError:
+                    pass
     mr = lambda s: rays_per_step * n / s / 1e6
     out = {
         "value": mr(pipe_s), "unit": "Mrays/s",
