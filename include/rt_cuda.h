@@ -354,6 +354,9 @@ int rt_cuda_debug_set_concurrent_sweep(int on);
  * renders; 1 = render, then copy; a negative count forces exactly that many bands whatever the
  * frame size.  Frames must be identical. */
 int rt_cuda_debug_set_sync_bands(int bands);
+/* Test knob: 1 (default) = launches of 60 000 tiles or more (about 1080p) over a linear-scan scene use the
+ * queued kernel's build with 7 CTAs per SM; 0 = always the 6-CTA build.  Frames must be identical. */
+int rt_cuda_debug_set_queued_dense(int on);
 /* Unit probe of the longest-tiles-first order: tiles_x*tiles_y tiles ordered by the costs of a map
  * that is 1 << shift times coarser (stable: costly classes first, image order within a class). */
 int rt_cuda_debug_tile_order(const uint32_t *cost, int cost_tiles_x, int cost_tiles_y, int shift,

@@ -156,6 +156,7 @@ struct Context {
 	unsigned  scene_epoch = 0;          /* bumped by every scene upload (tile schedules die with the scene) */
 	int       tile_schedule = 1;        /* 0: never reorder tiles (tests / A-B) */
 	int       concurrent_sweep = 1;     /* 0: rt_cuda_render_sweep runs its passes one after the other (tests / A-B) */
+	int       queued_dense = 1;         /* 0: never take the queued kernel's 7-CTA build (tests / A-B) */
 	int       sync_bands = 4;           /* most row bands of a synchronous call with a host frame; 1 = render, then copy */
 	bool      sync_bands_forced = false;/* tests: exactly that many, whatever the frame size */
 };
@@ -979,6 +980,7 @@ struct LaunchExtra {
 	bool  no_schedule = false;   /* leave the pose's tile schedule alone (launches that overlap one another) */
 	float grid_share = 1.0f;     /* persistent kernels: fraction of the resident CTA slots this launch may take */
 	bool  no_clear = false;      /* the never-written pixels of the CALL's band were cleared by an earlier launch of the call */
+	bool  no_dense = false;      /* keep the queued kernel's 6-CTA build (launches that share the SMs with other launches) */
 };
 
 static int launch_band(DeviceCtx &d, const RtCamera *cam, const PassPlan &pl, const RtRenderOpts *o,
@@ -1055,15 +1057,19 @@ static int launch_band(DeviceCtx &d, const RtCamera *cam, const PassPlan &pl, co
 			CU((pl.exact ? rt_exact_launch_render : rt_fast_launch_render)(&P, pl.lbvh, 2, grid, stream));
 			(*launches)++;
 		} else {
+		bool dense = false;
 		if (pl.persistent) {
 			CU(cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned int), stream));
 			/* occupancy of the persistent kernel, queried once per (variant, traversal, scene size) */
-			static int cached_per_sm[2][2][2] = {{{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}};
-			static int cached_n[2][2][2] = {{{-1, -1}, {-1, -1}}, {{-1, -1}, {-1, -1}}};
-			int &per_sm = cached_per_sm[pl.queued ? 1 : 0][pl.exact ? 0 : 1][pl.lbvh ? 1 : 0];
-			int &for_n = cached_n[pl.queued ? 1 : 0][pl.exact ? 0 : 1][pl.lbvh ? 1 : 0];
+			/* big launches of linear-scan scenes take the queued kernel's 7-CTA build (rt_render.cu) */
+			dense = pl.queued && !pl.lbvh && g.queued_dense && !X.no_dense && (size_t) P.tiles_x * (size_t) P.tiles_y >= 60000;
+			const int qk = pl.queued ? (dense ? 2 : 1) : 0;
+			static int cached_per_sm[3][2][2] = {};
+			static int cached_n[3][2][2] = {{{-1, -1}, {-1, -1}}, {{-1, -1}, {-1, -1}}, {{-1, -1}, {-1, -1}}};
+			int &per_sm = cached_per_sm[qk][pl.exact ? 0 : 1][pl.lbvh ? 1 : 0];
+			int &for_n = cached_n[qk][pl.exact ? 0 : 1][pl.lbvh ? 1 : 0];
 			if (per_sm < 1 || for_n != P.scene.n * 4096 + P.scene.num_runs) {
-				CU((pl.exact ? rt_exact_persistent_blocks_per_sm : rt_fast_persistent_blocks_per_sm)(&P, pl.lbvh, pl.queued ? 1 : 0, &per_sm));
+				CU((pl.exact ? rt_exact_persistent_blocks_per_sm : rt_fast_persistent_blocks_per_sm)(&P, pl.lbvh, qk, &per_sm));
 				if (per_sm < 1) per_sm = 1;
 				for_n = P.scene.n * 4096 + P.scene.num_runs;
 			}
@@ -1085,7 +1091,7 @@ static int launch_band(DeviceCtx &d, const RtCamera *cam, const PassPlan &pl, co
 				        P.tiles_x, P.tiles_y, pl.scale, (void *) P.tile_order, (void *) P.tile_cost, d.sched.cost_cur, d.sched.cost_scale,
 				        d.sched.order_cur, d.sched.order_scale, d.sched.order_from_scale);
 		}
-		CU((pl.exact ? rt_exact_launch_render : rt_fast_launch_render)(&P, pl.lbvh, pl.queued ? 3 : (pl.persistent ? 1 : 0), grid, stream));
+		CU((pl.exact ? rt_exact_launch_render : rt_fast_launch_render)(&P, pl.lbvh, pl.queued ? (dense ? 4 : 3) : (pl.persistent ? 1 : 0), grid, stream));
 		(*launches)++;
 		if (sched) tile_schedule_done(d, P, pl.scale, P.tiles_x, P.tiles_y, stream);
 		}
@@ -1635,6 +1641,7 @@ static int sweep_concurrent(const RtCamera *cam, void *fb, int w, int h, int ini
 		oo.accumulate = 0;
 		LaunchExtra X;
 		X.no_schedule = true;
+		X.no_dense = true;            /* measured: the 1080p sweep takes 0.98 ms with the scale-1 pass on the 7-CTA build, 0.83 ms without */
 		X.compact = !fine;
 		X.grid_share = fine ? 1.0f : sweep_grid_share(sc);
 		const int cpc = (column_w + sc - 1) / sc, cpr = ncols * cpc, lh = h / sc;
@@ -2116,6 +2123,13 @@ extern "C" int rt_cuda_debug_set_tile_schedule(int on)
 extern "C" int rt_cuda_debug_set_concurrent_sweep(int on)
 {
 	g.concurrent_sweep = on ? 1 : 0;
+	return RT_OK;
+}
+
+/* Test / A-B knob: 0 = big launches keep the queued kernel's 6-CTA build. */
+extern "C" int rt_cuda_debug_set_queued_dense(int on)
+{
+	g.queued_dense = on ? 1 : 0;
 	return RT_OK;
 }
 

@@ -566,9 +566,17 @@ __device__ __forceinline__ void rq_drain(const RtRenderParams &P, const SharedSc
 #ifndef RT_QUEUED_MIN_BLOCKS
 #define RT_QUEUED_MIN_BLOCKS 6
 #endif
+#ifndef RT_QUEUED_DENSE_BLOCKS
+#define RT_QUEUED_DENSE_BLOCKS 7
+#endif
 
-template <bool LBVH>
-__global__ void __launch_bounds__(RT_BLOCK_THREADS, LBVH ? RT_LBVH_QUEUED_MIN_BLOCKS : RT_QUEUED_MIN_BLOCKS)
+/* DENSE: the build for big launches of linear-scan scenes: 7 CTAs per SM at 72 registers, contrib /
+ * result parked in shared memory while a lane traces (path_park: without it 72 registers spill in
+ * the scan).  4K scene_0 1.887 -> 1.842 ms alone, 1.877 -> 1.831 ms per frame with three frames in
+ * flight; small launches (a 720p frame, 1/8 of a 4K frame) are 4 % slower alone -- more warps, fewer
+ * tiles each, a longer tail -- and the same in flight, so rt_api.cu picks this build from ~1080p up. */
+template <bool LBVH, bool DENSE = false>
+__global__ void __launch_bounds__(RT_BLOCK_THREADS, LBVH ? RT_LBVH_QUEUED_MIN_BLOCKS : (DENSE ? RT_QUEUED_DENSE_BLOCKS : RT_QUEUED_MIN_BLOCKS))
 render_queued_kernel(const __grid_constant__ RtRenderParams P)
 {
 	extern __shared__ __align__(16) unsigned char smem[];
@@ -580,7 +588,7 @@ render_queued_kernel(const __grid_constant__ RtRenderParams P)
 	const unsigned full = 0xffffffffu;
 	const unsigned lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
 	const unsigned total = (unsigned) (P.tiles_x * P.tiles_y) * 32u;
-	constexpr bool QPARK = !LBVH && RT_QUEUED_PARK;
+	constexpr bool QPARK = !LBVH && (DENSE || RT_QUEUED_PARK);
 
 	Path p;
 	p.mode = MODE_IDLE;
@@ -1155,6 +1163,12 @@ extern "C" cudaError_t RT_FN(launch_render)(const RtRenderParams *P, int lbvh, i
 		}
 		return cudaGetLastError();
 	}
+	if (persistent == 4) {      /* the queued kernel's build for big launches of linear-scan scenes */
+		size_t qsm = queued_smem_bytes(*P, false);
+		if ((e = allow_smem(render_queued_kernel<false, true>, qsm)) != cudaSuccess) return e;
+		render_queued_kernel<false, true><<<grid_blocks, RT_BLOCK_THREADS, qsm, stream>>>(*P);
+		return cudaGetLastError();
+	}
 	if (persistent == 2) {      /* wavefront kernel: one CTA per SM, paths pooled in shared memory */
 		size_t wsm = wavefront_smem_bytes(*P, lbvh != 0);
 		if (lbvh) {
@@ -1213,6 +1227,10 @@ extern "C" cudaError_t RT_FN(persistent_blocks_per_sm)(const RtRenderParams *P, 
 		if (lbvh) {
 			if ((e = allow_smem(render_queued_kernel<true>, sm)) != cudaSuccess) return e;
 			return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, render_queued_kernel<true>, RT_BLOCK_THREADS, sm);
+		}
+		if (queued == 2) {
+			if ((e = allow_smem(render_queued_kernel<false, true>, sm)) != cudaSuccess) return e;
+			return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, render_queued_kernel<false, true>, RT_BLOCK_THREADS, sm);
 		}
 		if ((e = allow_smem(render_queued_kernel<false>, sm)) != cudaSuccess) return e;
 		return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, render_queued_kernel<false>, RT_BLOCK_THREADS, sm);

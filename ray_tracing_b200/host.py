@@ -149,6 +149,7 @@ EXPORTED_SYMBOLS = [
     "rt_cuda_debug_set_light_anyhit",
     "rt_cuda_debug_set_concurrent_sweep",
     "rt_cuda_debug_set_sync_bands",
+    "rt_cuda_debug_set_queued_dense",
     "rt_cuda_param_bytes",
     "rt_cuda_set_progressive",
     "rt_cuda_invalidate_accumulation",
@@ -230,6 +231,7 @@ def load_library() -> C.CDLL:
     L.rt_cuda_debug_set_light_anyhit.argtypes = [C.c_int]
     L.rt_cuda_debug_set_concurrent_sweep.argtypes = [C.c_int]
     L.rt_cuda_debug_set_sync_bands.argtypes = [C.c_int]
+    L.rt_cuda_debug_set_queued_dense.argtypes = [C.c_int]
     L.rt_cuda_gl_register_buffer.argtypes = [C.c_uint, C.c_size_t]
     L.rt_cuda_gl_update_frame.argtypes = [C.POINTER(RtCamera), C.c_int, C.c_int, C.c_double, C.POINTER(RtRenderOpts), C.POINTER(RtRenderStats)]
     L.rt_cuda_gl_render_frame.argtypes = [C.POINTER(RtCamera), C.c_int, C.c_int, C.POINTER(RtRenderOpts), C.POINTER(RtRenderStats)]
@@ -651,6 +653,9 @@ class Renderer:
         """False / 0: tiles in image order; True / 1 (default): longest tiles first from the costs recorded at
         the pass's own scale; 2: finer passes are also seeded by coarser ones."""
         _check(self.lib.rt_cuda_debug_set_tile_schedule(2 if (on == 2 and on is not True) else (1 if on else 0)))
+
+    def set_queued_dense(self, on: bool) -> None:
+        _check(self.lib.rt_cuda_debug_set_queued_dense(1 if on else 0))
 
     def set_sync_bands(self, bands: int) -> None:
         _check(self.lib.rt_cuda_debug_set_sync_bands(int(bands)))

@@ -69,6 +69,21 @@ def test_bench_frames_equal_the_reference(renderer, stb_sky, gold, config, kerne
     assert sha(frame) == gold["frames"][config], (config, kernel)
 
 
+def test_both_builds_of_the_queued_kernel_give_the_bench_frame(renderer, stb_sky, gold):
+    """Launches of 60 000 tiles and more run the queued kernel's 7-CTA build (72 registers, contrib /
+    result parked in shared memory), smaller ones the 6-CTA build; the 4K bench frame from both."""
+    cfg = bench.CONFIGS["3"]
+    renderer.upload_skybox(stb_sky)
+    renderer.upload_scene(host.parse_scene_string(bench.scene_text(cfg)))
+    try:
+        for dense in (False, True):
+            renderer.set_queued_dense(dense)
+            frame, st = renderer.render_frame(Camera(), cfg["w"], cfg["h"], 1, kernel=RT_KERNEL_QUEUED)
+            assert sha(frame) == gold["frames"]["3"], dense
+    finally:
+        renderer.set_queued_dense(True)
+
+
 @pytest.fixture(scope="module")
 def spheres():
     return host.parse_scene_string_large(bench.scene_text(bench.CONFIGS["5"]))
