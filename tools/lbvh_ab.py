@@ -26,7 +26,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--tag", default="")
     ap.add_argument("--sizes", default="1920x1080,3840x2160")
-    ap.add_argument("--one", action="store_true", help="render the first size with the first kernel three times and exit (for ncu)")
+    ap.add_argument("--one", action="store_true", help="render the first size with the first kernel four times and exit (for ncu: -s 3 -c 1 takes an ordered launch)")
     ap.add_argument("--counts", default=None, help="counter build (-DRT_COUNT_WALK): write nodes / tests per ray of the last size to this JSON file")
     ap.add_argument("--no-anyhit", action="store_true", help="light samples walk to their nearest hit (rt_lbvh_debug_set_anyhit(0))")
     a = ap.parse_args()
@@ -47,7 +47,7 @@ def main():
     frame = torch.zeros((max(h for _, h in sizes), max(w for w, _ in sizes), 3), dtype=torch.float32, device="cuda")
     if a.one:
         w, h = sizes[0]
-        for _ in range(3):
+        for _ in range(4):          # records tile costs, builds the order, then two ordered launches
             r.render_into(cam, frame.data_ptr(), w, h, stats=True, kernel=K[a.kernels.split(",")[0]])
         r.close()
         return
