@@ -280,10 +280,16 @@ int rt_cuda_copy_async(void *dst, const void *src, size_t bytes, void *stream);
  *                                                      accum = 0, generation++, back to init_scale
  *   rt_cuda_update_frame(cam, fb, w, h, budget_ms,...)  update_frame() (main.c:450-482): at least one
  *       pass at the current scale (halving after each, main.c:402-403), then more passes while the
- *       device time spent stays within budget_ms (0 = exactly one pass); fb = accum / count. */
+ *       device time spent stays within budget_ms (0 = exactly one pass; negative = refine the pose to
+ *       full resolution: every remaining pass of the ladder down to scale 1, or one pass when it is
+ *       there already); fb = accum / count.  A fresh pose whose whole ladder fits the budget runs
+ *       its passes side by side (as rt_cuda_render_sweep does): same pass indices, same frame. */
 int      rt_cuda_set_progressive(int init_scale, int num_columns);
 int      rt_cuda_invalidate_accumulation(void);
 uint32_t rt_cuda_accum_generation(void);
+/* pass index (the RNG key of SURVEY.md R7's per-pixel stream) of the next rt_cuda_update_frame() pass;
+ * it keeps counting across invalidations, so a pose revisited draws fresh samples */
+uint64_t rt_cuda_next_pass_index(void);
 int      rt_cuda_update_frame(const RtCamera *cam, void *fb, int w, int h, double budget_ms,
                               const RtRenderOpts *opts, RtRenderStats *stats);
 

@@ -150,6 +150,7 @@ EXPORTED_SYMBOLS = [
     "rt_cuda_debug_set_concurrent_sweep",
     "rt_cuda_debug_set_sync_bands",
     "rt_cuda_debug_set_queued_dense",
+    "rt_cuda_next_pass_index",
     "rt_cuda_param_bytes",
     "rt_cuda_set_progressive",
     "rt_cuda_invalidate_accumulation",
@@ -232,6 +233,7 @@ def load_library() -> C.CDLL:
     L.rt_cuda_debug_set_concurrent_sweep.argtypes = [C.c_int]
     L.rt_cuda_debug_set_sync_bands.argtypes = [C.c_int]
     L.rt_cuda_debug_set_queued_dense.argtypes = [C.c_int]
+    L.rt_cuda_next_pass_index.restype = C.c_uint64
     L.rt_cuda_gl_register_buffer.argtypes = [C.c_uint, C.c_size_t]
     L.rt_cuda_gl_update_frame.argtypes = [C.POINTER(RtCamera), C.c_int, C.c_int, C.c_double, C.POINTER(RtRenderOpts), C.POINTER(RtRenderStats)]
     L.rt_cuda_gl_render_frame.argtypes = [C.POINTER(RtCamera), C.c_int, C.c_int, C.POINTER(RtRenderOpts), C.POINTER(RtRenderStats)]
@@ -573,6 +575,9 @@ class Renderer:
 
     def accum_generation(self) -> int:
         return self.lib.rt_cuda_accum_generation()
+
+    def next_pass_index(self) -> int:
+        return int(self.lib.rt_cuda_next_pass_index())
 
     def update_frame(self, camera: Camera, w: int, h: int, budget_ms: float = 0.0, *, out=None, **opts):
         o = self._opts(**opts)

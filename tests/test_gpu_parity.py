@@ -382,6 +382,51 @@ def test_concurrent_sweep_equals_sequential_passes(renderer, small_sky, builtin_
         renderer.set_concurrent_sweep(True)
 
 
+def test_update_frame_refines_a_fresh_pose_in_one_call(renderer, port, small_sky, builtin_objects):
+    """rt_cuda_update_frame with a negative budget renders every remaining pass of the ladder; for a
+    fresh pose the passes run side by side (sweep_concurrent).  Frame, weight and the passes that
+    follow must equal the reference's one-pass-at-a-time schedule (main.c:354, 402-403), with the
+    concurrent ladder and without it."""
+    W, H = 192, 108
+    renderer.upload_skybox(small_sky)
+    renderer.upload_scene(builtin_objects[0])
+    world = port.world(builtin_objects[0], small_sky)
+    def ladder(p0):
+        acc = np.zeros((H, W, 3), np.float32)
+        count = np.float32(0)
+        for k, s in enumerate((8, 4, 2, 1)):
+            data, _ = port.render(world, W, H, s, 1, p0 + k)
+            port.accumulate(acc, data, s)
+            count = np.float32(count + np.float32(1.0) / np.float32(s * s))
+        return acc, count
+
+    try:
+        for concurrent in (True, False):
+            renderer.set_concurrent_sweep(concurrent)
+            renderer.set_progressive(8, 1)
+            renderer.invalidate_accumulation()
+            p0 = renderer.next_pass_index()
+            acc, count = ladder(p0)
+            frame, st = renderer.update_frame(Camera(), W, H, budget_ms=-1.0)
+            assert np.array_equal(bits(frame), bits(port.resolve(acc, count))), concurrent
+            assert renderer.accum_count() == count and renderer.next_pass_index() == p0 + 4
+            frame, st = renderer.update_frame(Camera(), W, H, budget_ms=-1.0)      # at scale 1: exactly one more pass
+            data, _ = port.render(world, W, H, 1, 1, p0 + 4)
+            port.accumulate(acc, data, 1)
+            assert np.array_equal(bits(frame), bits(port.resolve(acc, np.float32(count + np.float32(1))))), concurrent
+            # stopped after the first pass of the ladder: the rest of it, one pass after the other
+            renderer.invalidate_accumulation()
+            p0 = renderer.next_pass_index()
+            acc, count = ladder(p0)
+            renderer.update_frame(Camera(), W, H, budget_ms=0.0)                  # the scale-8 pass
+            frame, st = renderer.update_frame(Camera(), W, H, budget_ms=-1.0)
+            assert np.array_equal(bits(frame), bits(port.resolve(acc, count))), concurrent
+    finally:
+        renderer.set_concurrent_sweep(True)
+        renderer.set_progressive(8, 1)
+        renderer.invalidate_accumulation()
+
+
 def test_banded_host_readback_changes_nothing(renderer, small_sky, builtin_objects):
     """A synchronous call with a host frame renders the frame as row bands and copies band k
     while band k+1 renders (rt_api.cu: render_pass).  1, 4 and 8 bands must give the same
@@ -422,10 +467,9 @@ def test_update_frame_loop_matches_reference_scheduler(renderer, port, small_sky
     world = port.world(builtin_objects[0], small_sky)
     renderer.set_progressive(8, 4)
     renderer.invalidate_accumulation()
-    gen = renderer.accum_generation()
     acc = np.zeros((H, W, 3), np.float32)
     count = np.float32(0)
-    p = 0
+    p = renderer.next_pass_index()        # the pass counter runs on across tests and invalidations
     frames = []
     for s in (8, 4, 2, 1, 1):
         frame, st = renderer.update_frame(Camera(), W, H, 0.0)
@@ -435,6 +479,7 @@ def test_update_frame_loop_matches_reference_scheduler(renderer, port, small_sky
         count = np.float32(count + np.float32(1.0) / np.float32(s * s))
         assert np.array_equal(bits(frame), bits(port.resolve(acc, count))), s
     # camera moved: back to init_scale, accum cleared, generation bumped
+    gen = renderer.accum_generation()     # (a frame size other than the last call's had bumped it once more before)
     renderer.invalidate_accumulation()
     assert renderer.accum_generation() == gen + 1 and renderer.accum_count() == 0.0
     cam = Camera((4.5, 4.5, 4.5), (-1, -1, -1), (0, 1, 0), 30.0)
