@@ -18,7 +18,7 @@ NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Iinclude -I$(SRC) -Xcompiler -fPI
 # host C: the reference's own flags matter for float parity (no contraction)
 CFLAGS    := -std=c11 -O2 -fPIC -ffp-contract=off -Wall -Wextra -Iinclude -I$(SRC)
 
-HOST_OBJS := $(OBJ)/scene_parse.o $(OBJ)/camera_host.o $(OBJ)/scene_pack.o $(OBJ)/screenshot.o
+HOST_OBJS := $(OBJ)/scene_parse.o $(OBJ)/camera_host.o $(OBJ)/scene_pack.o $(OBJ)/screenshot.o $(OBJ)/bvh_sah.o
 CUDA_OBJS := $(OBJ)/rt_api.o $(OBJ)/rt_lbvh.o $(OBJ)/rt_render_exact.o $(OBJ)/rt_render_fast.o
 DEVICE_HDRS := $(SRC)/rt_device.cuh $(SRC)/rt_params.h $(SRC)/rt_host.h $(SRC)/rt_lbvh.h $(SRC)/rt_lbvh_rule.h include/rt_cuda.h
 

@@ -164,6 +164,15 @@ int  rt_cuda_upload_skybox(const RtCubemap *sky);
 
 #define RT_LBVH_THRESHOLD 64
 
+/* Who shapes the tree of the NEXT rt_cuda_upload_scene / rt_cuda_upload_objects of a large scene.
+ * Either way the frames are the reference's, bit for bit (the walk applies scene.c:79-134 per
+ * primitive and breaks ties by index); the topology only decides how many nodes a ray visits. */
+enum { RT_BVH_BUILDER_SAH  = 0,   /* default: binned surface-area heuristic on the host (threads), ~40 ms per 100 000
+                                     primitives; BASELINE config 5 renders 8-9 % faster than with the Karras tree */
+       RT_BVH_BUILDER_LBVH = 1 }; /* Morton order + Karras hierarchy, entirely on the device (~1 ms of kernels):
+                                     for scenes rebuilt every frame */
+int  rt_cuda_set_bvh_builder(int builder);
+
 /* ------------------------------------------------------------------------- */
 /* Rendering                                                                 */
 /* ------------------------------------------------------------------------- */

@@ -329,6 +329,7 @@ extern "C" int rt_cuda_upload_objects(const RtObject *objects, int n)
 	g.have_scene = false;
 	g.have_bvh = false;
 	g.scene_epoch++;
+	rt_lbvh_drop_topology_cache();      /* keyed by this call's packed scene: never reuse an older one */
 	for (int i = 0; i < g.ngpu; i++) {
 		DeviceCtx &d = g.dev[i];
 		if ((rc = select_device(d)) != RT_OK) { rt_host_free_packed(&ps); return rc; }
@@ -367,6 +368,7 @@ extern "C" int rt_cuda_upload_objects(const RtObject *objects, int n)
 	g.num_runs = (int) runs.size();
 	g.have_scene = true;
 	g.have_bvh = want_bvh;
+	rt_lbvh_drop_topology_cache();
 	rt_host_free_packed(&ps);
 	cudaSetDevice(g.dev[0].device);
 	return RT_OK;
@@ -2139,6 +2141,14 @@ extern "C" int rt_cuda_debug_set_sync_bands(int bands)
 	g.sync_bands_forced = bands < 0;            /* negative: exactly -bands bands whatever the frame size (tests) */
 	if (bands < 0) bands = -bands;
 	g.sync_bands = bands < 1 ? 1 : (bands > RT_SYNC_BANDS_MAX ? RT_SYNC_BANDS_MAX : bands);
+	return RT_OK;
+}
+
+extern "C" void rt_lbvh_set_builder(int builder);
+extern "C" int rt_cuda_set_bvh_builder(int builder)
+{
+	if (builder != RT_BVH_BUILDER_SAH && builder != RT_BVH_BUILDER_LBVH) return fail(RT_ERR_ARG, "unknown BVH builder %d", builder);
+	rt_lbvh_set_builder(builder);
 	return RT_OK;
 }
 

@@ -1,6 +1,9 @@
 /*
- * rt_lbvh.cu -- device LBVH build (Morton codes -> radix sort -> Karras 2012
- * hierarchy -> bottom-up refit) for scenes above RT_LBVH_THRESHOLD objects.
+ * rt_lbvh.cu -- BVH build for scenes above RT_LBVH_THRESHOLD objects.  Topology: by
+ * default the host's binned-SAH builder (bvh_sah.c; 11 % fewer nodes per ray on
+ * BASELINE config 5), or entirely on the device (RT_BVH_BUILDER_LBVH: Morton codes
+ * -> radix sort -> Karras 2012 hierarchy).  Boxes (bottom-up refit), 16-bit packing
+ * and leaf records are made on the device either way.
  *
  * Parity contract: traversal (rt_device.cuh: walk_nodes / walk_leaf) must return
  * what the reference's linear scan (scene.c:156-173) returns, bit for bit.  The
@@ -45,6 +48,19 @@ extern "C" void rt_lbvh_debug_set(double k, double slack) { g_fuzz_k = k; g_slac
 /* test / A-B knob: 0 = light samples walk to their nearest hit like every other ray */
 static int g_anyhit = 1;
 extern "C" void rt_lbvh_debug_set_anyhit(int on) { g_anyhit = on ? 1 : 0; }
+/* topology of the next build: RT_BVH_BUILDER_* (include/rt_cuda.h) */
+static int g_builder = RT_BVH_BUILDER_SAH;
+extern "C" void rt_lbvh_set_builder(int builder) { g_builder = builder; }
+extern "C" int rt_lbvh_get_builder(void) { return g_builder; }
+static struct { const void *key; int n; double fuzz_r2; int *prim; int *links; int depth; } g_topo = {nullptr, 0, 0.0, nullptr, nullptr, 0};
+void rt_lbvh_drop_topology_cache(void)
+{
+	free(g_topo.prim); free(g_topo.links);
+	g_topo.prim = g_topo.links = nullptr;
+	g_topo.key = nullptr; g_topo.n = 0;
+}
+extern "C" int rt_host_bvh_sah(const RtF4 *A, const RtF4 *B, int n, double fuzz_r2, float cube_pad, float extra,
+                               int *prim_index, int *children, int *parent, int *depth_out);
 
 /* ---- Morton keys -------------------------------------------------------- */
 
@@ -419,15 +435,46 @@ int rt_lbvh_build(RtLbvh *bvh, const float4 *geomA, const float4 *geomB, int n,
 	if (nn >= (1u << 30)) return lfail(RT_ERR_ARG, "the LBVH holds at most 2^30 primitives");
 	LCU(cudaMalloc(&bvh->leaves, sizeof(float4) * 2 * nn));
 
+	float3 lo = make_float3(hs->bounds_lo.x, hs->bounds_lo.y, hs->bounds_lo.z);
+	float3 ext = make_float3(hs->bounds_hi.x - lo.x, hs->bounds_hi.y - lo.y, hs->bounds_hi.z - lo.z);
+	int blocks = (n + 255) / 256;
+	if (g_builder == RT_BVH_BUILDER_SAH) {
+		/* topology from the host (bvh_sah.c: binned SAH over the padded boxes the refit below will
+		 * compute); boxes, packing and everything the walk reads are made on the device as for the
+		 * Karras tree */
+		double mag = fmax(fmax(fabs((double) bvh->lo.x), fabs((double) bvh->hi.x)),
+		                  fmax(fmax(fabs((double) bvh->lo.y), fabs((double) bvh->hi.y)),
+		                       fmax(fabs((double) bvh->lo.z), fabs((double) bvh->hi.z))));
+		RtLbvhPads pads = rt_lbvh_pads(mag, (double) rt_lbvh_default_dmax((double) ext.x, (double) ext.y, (double) ext.z), g_fuzz_k, g_slack);
+		size_t links = (2 * nn - 1) + 2 * (nn > 1 ? nn - 1 : 1);
+		/* one host build serves every device of an upload (rt_api.cu calls this once per GPU with the
+		 * same packed scene and drops the cache when the upload is over) */
+		if (g_topo.key != hs->geomA || g_topo.n != n || g_topo.fuzz_r2 != pads.fuzz_r2) {
+			rt_lbvh_drop_topology_cache();
+			g_topo.prim = (int *) malloc(sizeof(int) * nn);
+			g_topo.links = (int *) calloc(links, sizeof(int));
+			if (!g_topo.prim || !g_topo.links ||
+			    rt_host_bvh_sah(hs->geomA, hs->geomB, n, pads.fuzz_r2, pads.cube_pad, pads.extra, g_topo.prim,
+			                    g_topo.links + (2 * nn - 1), g_topo.links, &g_topo.depth) != 0) {
+				rt_lbvh_drop_topology_cache();
+				return lfail(RT_ERR_NOMEM, "out of host memory building the BVH topology of %d primitives", n);
+			}
+			g_topo.key = hs->geomA; g_topo.n = n; g_topo.fuzz_r2 = pads.fuzz_r2;
+		}
+		LCU(cudaMemcpyAsync(bvh->prim_index, g_topo.prim, sizeof(int) * nn, cudaMemcpyHostToDevice, stream));
+		LCU(cudaMemcpyAsync(bvh->parent, g_topo.links, sizeof(int) * links, cudaMemcpyHostToDevice, stream));
+		LCU(cudaStreamSynchronize(stream));
+		int depth = g_topo.depth;
+		bvh->depth = depth;
+		gather_leaves_kernel<<<blocks, 256, 0, stream>>>(bvh->prim_index, n, geomA, geomB, bvh->leaves);
+		LCU(cudaGetLastError());
+	} else {
 	Scratch keys_in, keys_out, temp;
 	LCU(cudaMalloc(&keys_in.p, sizeof(unsigned long long) * nn));
 	LCU(cudaMalloc(&keys_out.p, sizeof(unsigned long long) * nn));
 
-	float3 lo = make_float3(hs->bounds_lo.x, hs->bounds_lo.y, hs->bounds_lo.z);
-	float3 ext = make_float3(hs->bounds_hi.x - lo.x, hs->bounds_hi.y - lo.y, hs->bounds_hi.z - lo.z);
 	float3 inv = make_float3(ext.x > 0 ? 1.0f / ext.x : 0.0f, ext.y > 0 ? 1.0f / ext.y : 0.0f,
 	                         ext.z > 0 ? 1.0f / ext.z : 0.0f);
-	int blocks = (n + 255) / 256;
 	morton_kernel<<<blocks, 256, 0, stream>>>(geomA, geomB, n, lo, inv, (unsigned long long *) keys_in.p);
 	LCU(cudaGetLastError());
 
@@ -453,6 +500,7 @@ int rt_lbvh_build(RtLbvh *bvh, const float4 *geomA, const float4 *geomB, int n,
 		LCU(cudaMemcpyAsync(&bvh->depth, bvh->visit, sizeof(int), cudaMemcpyDeviceToHost, stream));
 	}
 	LCU(cudaStreamSynchronize(stream));
+	}
 	int rc = locate_emitter(bvh, hs->only_emitter, stream);
 	if (rc != RT_OK) return rc;
 

@@ -38,6 +38,8 @@ int  rt_lbvh_build(RtLbvh *bvh, const float4 *geomA, const float4 *geomB, int n,
 int  rt_lbvh_refit(RtLbvh *bvh, const float4 *geomA, const float4 *geomB, float d_max, cudaStream_t stream);
 int  rt_lbvh_update(RtLbvh *bvh, const float4 *geomA, const float4 *geomB, const RtPackedScene *host_scene, cudaStream_t stream);
 void rt_lbvh_free(RtLbvh *bvh);
+/* the host-built topology is kept between the per-device builds of one upload; call when the upload is over */
+void rt_lbvh_drop_topology_cache(void);
 RtBvhView rt_lbvh_view(const RtLbvh *bvh);
 const char *rt_lbvh_last_error(void);
 

@@ -278,7 +278,7 @@ __device__ __forceinline__ void stack_init(LocalStack &, const SharedScene &) {}
  * nobody walks any more, so that classify / sweep / launch run with a fuller warp.
  */
 #ifndef RT_WALK_ITERS
-#define RT_WALK_ITERS 8
+#define RT_WALK_ITERS 10    /* 4K config 5, same box: 8 / 9 / 10 / 11 / 12 / 14 nodes: 30.63 / 30.12 / 29.76 / 29.93 / 30.22 / 31.31 ms (profiles/r02_lbvh_ab_iters.jsonl) */
 #endif
 #ifndef RT_WALK_HOLD
 #define RT_WALK_HOLD 12     /* 4K config 5: 8 / 12 / 16 / 20 lanes: +3 % / 31.4 / 31.7 / 32.7 ms; 1 (no waiting): +17 % */

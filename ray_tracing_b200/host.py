@@ -27,6 +27,7 @@ RT_VARIANT_EXACT, RT_VARIANT_FAST = 0, 1
 RT_TRAVERSAL_AUTO, RT_TRAVERSAL_LINEAR, RT_TRAVERSAL_LBVH = 0, 1, 2
 RT_MEM_AUTO, RT_MEM_HOST, RT_MEM_DEVICE = 0, 1, 2
 RT_KERNEL_AUTO, RT_KERNEL_PIXEL, RT_KERNEL_PERSISTENT, RT_KERNEL_WAVEFRONT, RT_KERNEL_QUEUED = 0, 1, 2, 3, 4
+RT_BVH_BUILDER_SAH, RT_BVH_BUILDER_LBVH = 0, 1
 RT_UP, RT_DOWN, RT_LEFT, RT_RIGHT = 0, 1, 2, 3
 RT_LBVH_THRESHOLD = 64
 
@@ -147,6 +148,7 @@ EXPORTED_SYMBOLS = [
     "rt_cuda_debug_set_sweep_threshold",
     "rt_cuda_debug_set_tile_schedule",
     "rt_cuda_debug_set_light_anyhit",
+    "rt_cuda_set_bvh_builder",
     "rt_cuda_debug_set_concurrent_sweep",
     "rt_cuda_debug_set_sync_bands",
     "rt_cuda_debug_set_queued_dense",
@@ -230,6 +232,7 @@ def load_library() -> C.CDLL:
     L.rt_cuda_debug_set_sweep_threshold.argtypes = [C.c_float]
     L.rt_cuda_debug_set_tile_schedule.argtypes = [C.c_int]
     L.rt_cuda_debug_set_light_anyhit.argtypes = [C.c_int]
+    L.rt_cuda_set_bvh_builder.argtypes = [C.c_int]
     L.rt_cuda_debug_set_concurrent_sweep.argtypes = [C.c_int]
     L.rt_cuda_debug_set_sync_bands.argtypes = [C.c_int]
     L.rt_cuda_debug_set_queued_dense.argtypes = [C.c_int]
@@ -670,6 +673,10 @@ class Renderer:
 
     def set_light_anyhit(self, on: bool) -> None:
         _check(self.lib.rt_cuda_debug_set_light_anyhit(1 if on else 0))
+
+    def set_bvh_builder(self, builder: int) -> None:
+        """RT_BVH_BUILDER_SAH (host, default) or RT_BVH_BUILDER_LBVH (device) for the next scene upload."""
+        _check(self.lib.rt_cuda_set_bvh_builder(int(builder)))
 
     def debug_tile_order(self, cost: np.ndarray, shift: int, tiles_x: int, tiles_y: int) -> np.ndarray:
         cost = np.ascontiguousarray(cost, dtype=np.uint32)

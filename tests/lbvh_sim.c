@@ -102,6 +102,10 @@ static int delta(const uint64_t *k, int n, int i, int j)
 static float fmin2(float a, float b) { return fminf(a, b); }
 static float fmax2(float a, float b) { return fmaxf(a, b); }
 
+
+/* SIM_TOPOLOGY=sah: the product's host-built topology instead of the Karras hierarchy */
+#include "../ray_tracing_b200/csrc/bvh_sah.c"
+
 static void build(Tree *T, const RtoObject *obj, int n, int global_pad)
 {
 	memset(T, 0, sizeof(*T));
@@ -174,6 +178,21 @@ static void build(Tree *T, const RtoObject *obj, int n, int global_pad)
 		parent[right >= 0 ? right : (n - 1) + ~right] = i;
 	}
 	parent[0] = -1;
+	if (getenv("SIM_TOPOLOGY") && !strcmp(getenv("SIM_TOPOLOGY"), "sah") && n >= 2) {
+		double mag0 = 0;
+		for (int k = 0; k < 3; k++) mag0 = fmax(mag0, fmax(fabs(lo[k]), fabs(hi[k])));
+		RtLbvhPads p0 = rt_lbvh_pads(mag0, rt_lbvh_default_dmax(ext[0], ext[1], ext[2]), RT_LBVH_FUZZ_K, RT_LBVH_SLACK);
+		int sah_depth;
+		RtF4 *Bt = malloc(sizeof(RtF4) * n);               /* the device layout keeps the type as int bits in .w */
+		for (int i = 0; i < n; i++) {
+			int ty = B[i].w == 1 ? RT_OBJECT_SPHERE : RT_OBJECT_CUBE;
+			Bt[i] = (RtF4){B[i].x, B[i].y, B[i].z, 0};
+			memcpy(&Bt[i].w, &ty, 4);
+		}
+		if (rt_host_bvh_sah((const RtF4 *) A, Bt, n, p0.fuzz_r2, p0.cube_pad, p0.extra, T->prim, children, parent, &sah_depth)) exit(2);
+		free(Bt);
+		for (int i = 0; i < n - 1; i++) count[i] = n;      /* no SIM_LEAF collapsing on this topology */
+	}
 
 	for (int sl = 0; sl < n && n >= 2; sl++) {
 		int d = 0;

@@ -152,13 +152,53 @@ def test_deep_tree_takes_the_local_stack_kernel(renderer, port, small_sky):
     still equal the O(N) oracle."""
     objs = deep_tree_scene()
     renderer.upload_skybox(small_sky)
-    renderer.upload_scene(objs)
     cam = Camera((9.0, 6.0, 14.0), (-0.5, -0.35, -1.0), (0, 1, 0), 30.0)
     want, rays = port.render(port.world(objs, small_sky, cam.as_dict()), 160, 90, 1, 1, 0)
     assert rays > 160 * 90
-    for kern in KERNELS.values():
-        frame, st = renderer.render_frame(cam, 160, 90, 1, kernel=kern)
-        assert np.array_equal(frame.view(np.uint32), want.view(np.uint32)) and st["rays"] == rays
+    try:
+        # the depth is a property of the Karras tree (the host's SAH builder splits this scene evenly)
+        for builder in (host.RT_BVH_BUILDER_LBVH, host.RT_BVH_BUILDER_SAH):
+            renderer.set_bvh_builder(builder)
+            renderer.upload_scene(objs)
+            for kern in KERNELS.values():
+                frame, st = renderer.render_frame(cam, 160, 90, 1, kernel=kern)
+                assert np.array_equal(frame.view(np.uint32), want.view(np.uint32)) and st["rays"] == rays, (builder, kern)
+    finally:
+        renderer.set_bvh_builder(host.RT_BVH_BUILDER_SAH)
+
+
+def test_both_bvh_builders_give_the_reference_frame(renderer, port, small_sky):
+    """rt_cuda_set_bvh_builder: host SAH topology (default) and device Morton/Karras topology walk
+    to the same hits as the reference's O(N) scan -- a mixed scene of cubes and spheres with the
+    emitter in the middle of the index range, and spheres only; then objects move and the tree
+    is refitted (rt_cuda_update_objects keeps whichever topology was built)."""
+    from conftest import random_scene
+
+    mixed = random_scene(4000, seed=31, extent=14.0)
+    spheres = random_scene(6000, seed=32, spheres_only=True, extent=12.0)
+    cam = Camera((4.0, 5.0, 3.0), (-1.0, -0.6, -0.7), (0, 1, 0), 30.0)
+    renderer.upload_skybox(small_sky)
+    rng = np.random.default_rng(8)
+    try:
+        for objs in (mixed, spheres):
+            want, rays = port.render(port.world(objs, small_sky, cam.as_dict()), 192, 108, 1, 1, 0)
+            moved = objs.copy()
+            idx = rng.choice(len(objs), len(objs) // 50, replace=False)
+            moved["geom"][idx, :3] += np.round(rng.normal(scale=3.0, size=(len(idx), 3)), 3).astype(np.float32)
+            want_moved, rays_moved = port.render(port.world(moved, small_sky, cam.as_dict()), 192, 108, 1, 1, 0)
+            for builder in (host.RT_BVH_BUILDER_SAH, host.RT_BVH_BUILDER_LBVH):
+                renderer.set_bvh_builder(builder)
+                renderer.upload_scene(objs)
+                for kern in (RT_KERNEL_PERSISTENT, RT_KERNEL_QUEUED):
+                    frame, st = renderer.render_frame(cam, 192, 108, 1, kernel=kern)
+                    assert np.array_equal(frame.view(np.uint32), want.view(np.uint32)) and st["rays"] == rays, (builder, kern)
+                renderer.update_objects(moved)
+                frame, st = renderer.render_frame(cam, 192, 108, 1)
+                assert np.array_equal(frame.view(np.uint32), want_moved.view(np.uint32)) and st["rays"] == rays_moved, builder
+        with pytest.raises(host.RtError):
+            renderer.set_bvh_builder(7)
+    finally:
+        renderer.set_bvh_builder(host.RT_BVH_BUILDER_SAH)
 
 
 @pytest.mark.parametrize("seed,n,extent,cam", [

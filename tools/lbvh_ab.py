@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--sizes", default="1920x1080,3840x2160")
     ap.add_argument("--one", action="store_true", help="render the first size with the first kernel four times and exit (for ncu: -s 3 -c 1 takes an ordered launch)")
     ap.add_argument("--counts", default=None, help="counter build (-DRT_COUNT_WALK): write nodes / tests per ray of the last size to this JSON file")
+    ap.add_argument("--builder", default="sah", choices=["sah", "lbvh"], help="topology: host SAH (default) or device Morton/Karras (rt_cuda_set_bvh_builder)")
     ap.add_argument("--no-anyhit", action="store_true", help="light samples walk to their nearest hit (rt_lbvh_debug_set_anyhit(0))")
     a = ap.parse_args()
     import torch
@@ -40,8 +41,14 @@ def main():
     r = host.Renderer(num_gpus=1)
     if a.no_anyhit:
         r.set_light_anyhit(False)
+    r.set_bvh_builder(host.RT_BVH_BUILDER_SAH if a.builder == "sah" else host.RT_BVH_BUILDER_LBVH)
     r.upload_skybox(scenes.procedural_skybox(256, seed=11))
-    r.upload_scene(host.parse_scene_string_large(scenes.synthetic_spheres_text(a.n)))
+    import time
+    objs = host.parse_scene_string_large(scenes.synthetic_spheres_text(a.n))
+    t0 = time.perf_counter()
+    r.upload_scene(objs)
+    r.synchronize()
+    upload_ms = (time.perf_counter() - t0) * 1e3
     cam = host.Camera()
     sizes = [tuple(int(v) for v in s.split("x")) for s in a.sizes.split(",")]
     frame = torch.zeros((max(h for _, h in sizes), max(w for w, _ in sizes), 3), dtype=torch.float32, device="cuda")
@@ -52,7 +59,7 @@ def main():
         r.close()
         return
     for name in a.kernels.split(","):
-        out = {"kernel": name, "lib": a.lib or "default", "tag": a.tag, "n": a.n}
+        out = {"kernel": name, "lib": a.lib or "default", "tag": a.tag, "n": a.n, "builder": a.builder, "upload_ms": round(upload_ms, 1)}
         for w, h in sizes:
             ts, st = [], None
             frame.fill_(-1.0)
