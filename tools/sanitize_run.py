@@ -46,12 +46,14 @@ def main():
     r.synchronize()
     assert r.shared_frame_error(ptr) == 0
     r.shared_frame_close(ptr, owner=True)
-    r.upload_scene(host.parse_scene_string_large(scenes.synthetic_spheres_text(3000, seed=5)))
-    for anyhit in (True, False):                            # one emitter: light samples in any-hit mode; parked path state
-        r.set_light_anyhit(anyhit)
-        for k in (host.RT_KERNEL_PIXEL, host.RT_KERNEL_PERSISTENT, host.RT_KERNEL_WAVEFRONT, host.RT_KERNEL_QUEUED):
-            r.render_frame(cam, 160, 90, 1, kernel=k)
-    r.set_light_anyhit(True)
+    for builder in (host.RT_BVH_BUILDER_LBVH, host.RT_BVH_BUILDER_SAH):   # device Karras tree, then the host's SAH topology (the default)
+        r.set_bvh_builder(builder)
+        r.upload_scene(host.parse_scene_string_large(scenes.synthetic_spheres_text(3000, seed=5)))
+        for anyhit in (True, False):                        # one emitter: light samples in any-hit mode; parked path state
+            r.set_light_anyhit(anyhit)
+            for k in (host.RT_KERNEL_PIXEL, host.RT_KERNEL_PERSISTENT, host.RT_KERNEL_WAVEFRONT, host.RT_KERNEL_QUEUED):
+                r.render_frame(cam, 160, 90, 1, kernel=k)
+        r.set_light_anyhit(True)
     moved = host.parse_scene_string_large(scenes.synthetic_spheres_text(3000, seed=5))
     moved["geom"][::50, 0] += 1.5
     r.update_objects(moved)
