@@ -690,12 +690,15 @@ def main_gpu(args):
         muladd_peak = r.fp32_peak_tflops(False)
         peak = muladd_peak if exact else fma_peak
 
-        def fp32_roofline(c, rays, ms):
+        def fp32_roofline(c, rays, ms, gpus=1):
+            """`rays` in `ms` on `gpus` GPUs against `gpus` times the peak measured on this one"""
             fpr, counts = (CONFIGS[c]["flops_per_ray"], None) if CONFIGS[c]["flops_per_ray"] else lbvh_flops_per_ray()
             if not fpr:
                 return None
             ach = rays * fpr / (ms * 1e-3) / 1e12
-            d = {"bound": "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None, "flops_per_ray": fpr}
+            d = {"bound": "fp32", "achieved": ach, "peak": peak * gpus, "unit": "TFLOP/s", "frac": ach / (peak * gpus) if peak else None, "flops_per_ray": fpr}
+            if gpus > 1:
+                d["gpus"] = gpus
             if counts:
                 d["flops_per_ray_source"] = "15 + 24*nodes + 18*sphere tests per ray, counter build (profiles/r02_lbvh_counts.json): %.1f nodes, %.2f tests" % (counts["nodes_per_ray"], counts["tests_per_ray"])
             return d
@@ -719,7 +722,7 @@ def main_gpu(args):
                      "peak_source": "measured live: register-only %s chains on this GPU" % ("MUL+ADD (no-FMA exact build)" if exact else "FMA"),
                      "fp32_fma_peak_tflops": fma_peak, "fp32_muladd_peak_tflops": muladd_peak})
         for c, m in others.items():
-            m["roofline"] = fp32_roofline(c, m["rays_per_step"], m["ms_per_step"])
+            m["roofline"] = fp32_roofline(c, m["rays_per_step"], m["ms_per_step"], world)      # whole-job rays over all ranks
         composite = "none (1 GPU)" if world == 1 else (
             "pipelined P2P: every rank renders its 16-row blocks (round robin) into one of two local frames and ships them with one strided "
             "peer copy on its copy stream into rank 0's frame over NVLink (cudaIpc mapping) while the next frame renders; a flag word per rank in "

@@ -1,4 +1,4 @@
-ncu --set full --clock-control none --import-source on -k regex:render_persistent -s 3 -c 1 -f -o gpurun_out/r02m_lbvh_persistent_4k python tools/lbvh_ab.py --one --sizes 3840x2160 --kernels persistent > gpurun_out/ncu_m.log 2>&1
-tail -3 gpurun_out/ncu_m.log
-(echo "--- memcheck"; timeout 600 compute-sanitizer --tool memcheck python tools/sanitize_run.py 2>&1 | tail -4; echo "--- racecheck"; timeout 600 compute-sanitizer --tool racecheck python tools/sanitize_run.py 2>&1 | tail -4) > gpurun_out/r02m_sanitizer.txt
-cat gpurun_out/r02m_sanitizer.txt
+timeout 300 python -m pytest tests/test_multi_gpu.py -m gpu -x -q > gpurun_out/r02m_pytest_mg.log 2>&1
+tail -3 gpurun_out/r02m_pytest_mg.log
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 > gpurun_out/r02m_scale_n2.json 2> gpurun_out/r02m_scale_n2.err
+tail -c 1500 gpurun_out/r02m_scale_n2.json; tail -3 gpurun_out/r02m_scale_n2.err
