@@ -1,4 +1,5 @@
-timeout 300 python -m pytest tests/test_multi_gpu.py -m gpu -x -q > gpurun_out/r02m_pytest_mg.log 2>&1
-tail -3 gpurun_out/r02m_pytest_mg.log
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 > gpurun_out/r02m_scale_n2.json 2> gpurun_out/r02m_scale_n2.err
-tail -c 1500 gpurun_out/r02m_scale_n2.json; tail -3 gpurun_out/r02m_scale_n2.err
+timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "banded or sync or update_frame or headless" > gpurun_out/r02n_pytest_sync.log 2>&1
+tail -5 gpurun_out/r02n_pytest_sync.log
+timeout 300 python tools/sync_ab.py > gpurun_out/r02n_sync_ab.jsonl 2> gpurun_out/r02n_sync_ab.err
+cat gpurun_out/r02n_sync_ab.jsonl; tail -3 gpurun_out/r02n_sync_ab.err
+RT_PROGRESS_DEBUG=1 timeout 100 python tools/_dbg_progress.py 2>&1 | tail -12
