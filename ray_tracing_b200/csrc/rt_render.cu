@@ -278,7 +278,8 @@ __device__ __forceinline__ void stack_init(LocalStack &, const SharedScene &) {}
  * nobody walks any more, so that classify / sweep / launch run with a fuller warp.
  */
 #ifndef RT_WALK_ITERS
-#define RT_WALK_ITERS 10    /* 4K config 5, same box: 8 / 9 / 10 / 11 / 12 / 14 nodes: 30.63 / 30.12 / 29.76 / 29.93 / 30.22 / 31.31 ms (profiles/r02_lbvh_ab_iters.jsonl) */
+#define RT_WALK_ITERS 9     /* 4K config 5, same box, Karras tree: 8 / 9 / 10 / 11 / 12 / 14 nodes: 30.63 / 30.12 / 29.76 / 29.93 / 30.22 / 31.31 ms;
+                             * SAH tree (fewer nodes per ray): 9 / 10 / 11 / 12: 27.78 / 28.02 / 28.49 / 29.10 ms (profiles/r02_lbvh_ab_iters.jsonl) */
 #endif
 #ifndef RT_WALK_HOLD
 #define RT_WALK_HOLD 12     /* 4K config 5: 8 / 12 / 16 / 20 lanes: +3 % / 31.4 / 31.7 / 32.7 ms; 1 (no waiting): +17 % */
@@ -844,7 +845,7 @@ render_wavefront_kernel(const __grid_constant__ RtRenderParams P)
 	extern __shared__ __align__(16) unsigned char smem[];
 	SharedScene S = stage_scene(P, smem, !LBVH);
 	size_t scene_bytes = RT_SCENE_HEAD_BYTES +
-	                     (LBVH ? sizeof(int) * (RT_SMEM_STACK + 1) * RT_BLOCK_THREADS
+	                     (LBVH ? sizeof(int) * RT_SMEM_STACK_ENTRIES(P.bvh.depth) * RT_BLOCK_THREADS
 	                           : 2 * sizeof(float4) * (size_t) P.scene.n + sizeof(int2) * (size_t) P.scene.num_runs);
 	scene_bytes = (scene_bytes + 15) & ~(size_t) 15;
 	const unsigned full = 0xffffffffu;
@@ -1115,7 +1116,7 @@ __global__ void probe_div_kernel(uint64_t seed, unsigned per_thread, int lo_exp_
 static size_t smem_bytes(const RtRenderParams &P, bool lbvh)
 {
 	return RT_SCENE_HEAD_BYTES +
-	       (lbvh ? sizeof(int) * (RT_SMEM_STACK + 1) * RT_BLOCK_THREADS      /* traversal stacks */
+	       (lbvh ? sizeof(int) * RT_SMEM_STACK_ENTRIES(P.bvh.depth) * RT_BLOCK_THREADS      /* traversal stacks */
 	             : 2 * sizeof(float4) * (size_t) P.scene.n + sizeof(int2) * (size_t) P.scene.num_runs);
 }
 

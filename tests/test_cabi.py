@@ -84,3 +84,12 @@ def test_missing_library_fails_loudly(monkeypatch):
     assert "no pure-Python or CPU rendering path" in str(e.value)
     with pytest.raises(ImportError):
         host.Renderer(num_gpus=1)
+
+
+def test_bvh_builder_knob_validates_its_argument():
+    """rt_cuda_set_bvh_builder needs no device: it only says who shapes the tree of the next upload."""
+    lib = host.load_library()
+    assert lib.rt_cuda_set_bvh_builder(host.RT_BVH_BUILDER_LBVH) == 0
+    assert lib.rt_cuda_set_bvh_builder(host.RT_BVH_BUILDER_SAH) == 0
+    assert lib.rt_cuda_set_bvh_builder(7) == -3            # RT_ERR_ARG
+    assert b"builder" in lib.rt_cuda_last_error()
