@@ -14,8 +14,9 @@
 #define RT_SMEM_STACK 32         /* most traversal-stack entries per thread in shared memory; deeper trees use the local-memory build */
 #endif
 /* A launch reserves what ITS tree needs: one entry per level (near-first traversal) and the sentinel.
- * BASELINE config 5 (depth 20): 10.8 instead of 16.9 KB per CTA, so eight CTAs leave the L1 124 instead
- * of 60 KB of the SM's 256 (the carve-out steps from 196 down to 132 KB): 28.02 -> 27.81 ms per 4K frame */
+ * BASELINE config 5 (depth 20): 10.5 instead of 16.5 KiB of stacks per CTA next to the 10.6 KiB head, so
+ * eight CTAs (plus 1 KiB each) need 177 instead of 225 KiB: the carve-out steps from 228 down to 196 KB
+ * and the L1 that serves the node fetches grows from 28 to 60 KB: 28.02 -> 27.81 ms per 4K frame */
 #define RT_SMEM_STACK_ENTRIES(depth) (((depth) < RT_SMEM_STACK ? (depth) : RT_SMEM_STACK) + 1)
 #define RT_TILE_W 8           /* a warp covers an 8x4 tile of low-res pixels */
 #define RT_TILE_H 4
