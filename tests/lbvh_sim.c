@@ -21,6 +21,10 @@
  * the bounds' diagonal).  --dynamic-pad = the measured-and-rejected alternative:
  * tight boxes, widened per visited node by the fuzz the actual distance from
  * the ray origin allows (see rt_lbvh_rule.h for the numbers).
+ * Environment: SIM_TOPOLOGY=sah|karras (the product's two builders), SIM_FMA / SIM_PACK (the device's
+ * slab arithmetic and 16-bit boxes), SIM_ANYHIT (light samples as the device walks them), SIM_AXIS,
+ * SIM_RAYS, SIM_DMAX, SIM_SLACK; experiments: SIM_LEAF (multi-primitive leaves), SIM_WIDE (what a
+ * 4-wide collapse of the tree would visit and test: DESIGN.md 8).
  */
 #define _GNU_SOURCE
 #include <float.h>
@@ -295,6 +299,8 @@ typedef struct { float t; int obj; } Best;
 /* rt_device.cuh: node_overlap with widened boxes */
 static int g_fma;       /* SIM_FMA: slab distances as fma(plane, inv, -(o*inv)) */
 
+static int g_wide;      /* SIM_WIDE */
+static long g_wide_boxes;
 static int g_packed;    /* the tree holds Q = 2^23 + q; o[] holds oi = fma(K, inv, o' * inv) (rt_device.cuh: walk_ray) */
 
 static int overlap(f4 lo, f4 hi, const float o[3], const float inv[3], float pad, float tmax, float *tn)
@@ -386,6 +392,36 @@ static void walk(const Tree *T, const RtoObject *obj, const float ray[6], Best *
 					}
 				}
 			}
+		} else if (g_wide) {
+			/* SIM_WIDE: what a 4-wide collapse of this tree would do (experiment for DESIGN.md 8): a visit
+			 * tests the boxes of the node's grandchildren (a child that is a leaf stands for itself), hit
+			 * ones are entered near-first.  nodes = wide-node visits, g_wide_boxes = boxes tested. */
+			(*nodes)++;
+			const f4 *nb = T->nodes + 4 * (size_t) node;
+			f4 clo[4], chi[4];
+			int32_t cid[4];
+			int nc = 0;
+			for (int side = 0; side < 2; side++) {
+				int32_t c;
+				memcpy(&c, &nb[2 * side].w, 4);
+				if (c < 0) { clo[nc] = nb[2 * side]; chi[nc] = nb[2 * side + 1]; cid[nc++] = c; }
+				else {
+					const f4 *cb = T->nodes + 4 * (size_t) c;
+					for (int s2 = 0; s2 < 2; s2++) { clo[nc] = cb[2 * s2]; chi[nc] = cb[2 * s2 + 1]; memcpy(&cid[nc], &cb[2 * s2].w, 4); nc++; }
+				}
+			}
+			float lim = best.t < FLT_MAX ? best.t + T->t_slack : FLT_MAX;
+			float tn[4];
+			int hit_i[4], nh = 0;
+			for (int i = 0; i < nc; i++) {
+				__atomic_add_fetch(&g_wide_boxes, 1, __ATOMIC_RELAXED);
+				if (overlap(clo[i], chi[i], o, inv, 0, lim, &tn[i])) hit_i[nh++] = i;
+			}
+			for (int i = 1; i < nh; i++)           /* near first */
+				for (int j = i; j > 0 && tn[hit_i[j]] < tn[hit_i[j - 1]]; j--) { int t = hit_i[j]; hit_i[j] = hit_i[j - 1]; hit_i[j - 1] = t; }
+			for (int i = nh - 1; i >= 1; i--) { stack_t[sp] = tn[hit_i[i]]; stack[sp++] = cid[hit_i[i]]; }
+			if (sp > *deepest) *deepest = sp;
+			if (nh) { node = cid[hit_i[0]]; continue; }
 		} else {
 			(*nodes)++;
 			const f4 *nb = T->nodes + 4 * (size_t) node;
@@ -447,6 +483,7 @@ int main(int argc, char **argv)
 	for (; argi < argc; argi++) if (!strcmp(argv[argi], "--dynamic-pad")) global_pad = 0;
 
 	g_fma = getenv("SIM_FMA") != NULL;
+	g_wide = getenv("SIM_WIDE") != NULL;
 	int axis_rays = getenv("SIM_AXIS") != NULL;    /* make some secondary rays (nearly) axis-parallel */
 	Tree T;
 	build(&T, obj, n, global_pad);
@@ -546,6 +583,7 @@ int main(int argc, char **argv)
 		is_shadow = next_shadow;
 		nr = m;
 	}
+	if (g_wide) fprintf(stderr, "wide walk: %.2f boxes tested per ray\n", (double) g_wide_boxes / total_rays);
 	printf("{\"objects\": %d, \"rays\": %ld, \"mismatches\": %ld, \"nodes_per_ray\": %.2f, \"tests_per_ray\": %.3f, \"deepest_stack\": %d, \"tree_depth\": %d, \"rule\": \"%s\"}\n",
 	       n, total_rays, mism, (double) nodes / total_rays, (double) tests / total_rays, deepest, T.depth, global_pad ? "static pad (product)" : "per-node pad (experiment)");
 	return mism != 0;
