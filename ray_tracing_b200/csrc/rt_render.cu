@@ -389,8 +389,12 @@ render_pixel_kernel(const __grid_constant__ RtRenderParams P)
  * and resident warps started to pay: BASELINE config 5 at 4K, persistent kernel, 5 / 6 / 7 / 8 / 9 /
  * 10 CTAs per SM (96 / 80 / 72 / 64 / 56 / 48 registers): 47.3 / 42.3 / 39.8 / 39.3 / 40.1 / 40.7 ms.
  * The queued kernel's extra shared memory (finish / refill queues) caps it at 5-6 CTAs: 44.5 ms. */
+/* Re-measured once the stacks were sized by the tree's depth (rt_params.h) and the tree came from the SAH
+ * builder: 7 CTAs x 72 registers (no spills; 155 KiB of shared memory: carve-out 164 KB, 92 KB of L1 for the
+ * node fetches) against 8 x 64 (62 bytes of spills, 177 KiB: carve-out 196 KB, 60 KB of L1): 26.64 against
+ * 27.55 ms (profiles/r02_lbvh_ab_iters.jsonl, tag b7). */
 #ifndef RT_LBVH_MIN_BLOCKS
-#define RT_LBVH_MIN_BLOCKS 8
+#define RT_LBVH_MIN_BLOCKS 7
 #endif
 #ifndef RT_LBVH_QUEUED_MIN_BLOCKS
 #define RT_LBVH_QUEUED_MIN_BLOCKS 5
