@@ -51,7 +51,6 @@ extern "C" void rt_lbvh_debug_set_anyhit(int on) { g_anyhit = on ? 1 : 0; }
 /* topology of the next build: RT_BVH_BUILDER_* (include/rt_cuda.h) */
 static int g_builder = RT_BVH_BUILDER_SAH;
 extern "C" void rt_lbvh_set_builder(int builder) { g_builder = builder; }
-extern "C" int rt_lbvh_get_builder(void) { return g_builder; }
 static struct { const void *key; int n; double fuzz_r2; int *prim; int *links; int depth; } g_topo = {nullptr, 0, 0.0, nullptr, nullptr, 0};
 void rt_lbvh_drop_topology_cache(void)
 {
@@ -464,42 +463,41 @@ int rt_lbvh_build(RtLbvh *bvh, const float4 *geomA, const float4 *geomB, int n,
 		LCU(cudaMemcpyAsync(bvh->prim_index, g_topo.prim, sizeof(int) * nn, cudaMemcpyHostToDevice, stream));
 		LCU(cudaMemcpyAsync(bvh->parent, g_topo.links, sizeof(int) * links, cudaMemcpyHostToDevice, stream));
 		LCU(cudaStreamSynchronize(stream));
-		int depth = g_topo.depth;
-		bvh->depth = depth;
+		bvh->depth = g_topo.depth;
 		gather_leaves_kernel<<<blocks, 256, 0, stream>>>(bvh->prim_index, n, geomA, geomB, bvh->leaves);
 		LCU(cudaGetLastError());
 	} else {
-	Scratch keys_in, keys_out, temp;
-	LCU(cudaMalloc(&keys_in.p, sizeof(unsigned long long) * nn));
-	LCU(cudaMalloc(&keys_out.p, sizeof(unsigned long long) * nn));
+		Scratch keys_in, keys_out, temp;
+		LCU(cudaMalloc(&keys_in.p, sizeof(unsigned long long) * nn));
+		LCU(cudaMalloc(&keys_out.p, sizeof(unsigned long long) * nn));
 
-	float3 inv = make_float3(ext.x > 0 ? 1.0f / ext.x : 0.0f, ext.y > 0 ? 1.0f / ext.y : 0.0f,
-	                         ext.z > 0 ? 1.0f / ext.z : 0.0f);
-	morton_kernel<<<blocks, 256, 0, stream>>>(geomA, geomB, n, lo, inv, (unsigned long long *) keys_in.p);
-	LCU(cudaGetLastError());
+		float3 inv = make_float3(ext.x > 0 ? 1.0f / ext.x : 0.0f, ext.y > 0 ? 1.0f / ext.y : 0.0f,
+		                         ext.z > 0 ? 1.0f / ext.z : 0.0f);
+		morton_kernel<<<blocks, 256, 0, stream>>>(geomA, geomB, n, lo, inv, (unsigned long long *) keys_in.p);
+		LCU(cudaGetLastError());
 
-	size_t temp_bytes = 0;
-	LCU(cub::DeviceRadixSort::SortKeys(nullptr, temp_bytes, (const unsigned long long *) keys_in.p,
-	                                   (unsigned long long *) keys_out.p, n, 0, 64, stream));
-	LCU(cudaMalloc(&temp.p, temp_bytes ? temp_bytes : 4));
-	LCU(cub::DeviceRadixSort::SortKeys(temp.p, temp_bytes, (const unsigned long long *) keys_in.p,
-	                                   (unsigned long long *) keys_out.p, n, 0, 64, stream));
-	unpack_index_kernel<<<blocks, 256, 0, stream>>>((const unsigned long long *) keys_out.p, n, geomA, geomB,
-	                                                bvh->prim_index, bvh->leaves);
-	LCU(cudaGetLastError());
-	if (n >= 2) {
-		hierarchy_kernel<<<blocks, 256, 0, stream>>>((const unsigned long long *) keys_out.p, n,
-		                                             g_children_of(bvh), bvh->parent);
+		size_t temp_bytes = 0;
+		LCU(cub::DeviceRadixSort::SortKeys(nullptr, temp_bytes, (const unsigned long long *) keys_in.p,
+		                                   (unsigned long long *) keys_out.p, n, 0, 64, stream));
+		LCU(cudaMalloc(&temp.p, temp_bytes ? temp_bytes : 4));
+		LCU(cub::DeviceRadixSort::SortKeys(temp.p, temp_bytes, (const unsigned long long *) keys_in.p,
+		                                   (unsigned long long *) keys_out.p, n, 0, 64, stream));
+		unpack_index_kernel<<<blocks, 256, 0, stream>>>((const unsigned long long *) keys_out.p, n, geomA, geomB,
+		                                                bvh->prim_index, bvh->leaves);
 		LCU(cudaGetLastError());
-	}
-	if (n >= 2) {
-		/* visit[0] doubles as the result cell (refit clears the array afterwards) */
-		LCU(cudaMemsetAsync(bvh->visit, 0, sizeof(unsigned int), stream));
-		depth_kernel<<<blocks, 256, 0, stream>>>(bvh->parent, n, (int *) bvh->visit);
-		LCU(cudaGetLastError());
-		LCU(cudaMemcpyAsync(&bvh->depth, bvh->visit, sizeof(int), cudaMemcpyDeviceToHost, stream));
-	}
-	LCU(cudaStreamSynchronize(stream));
+		if (n >= 2) {
+			hierarchy_kernel<<<blocks, 256, 0, stream>>>((const unsigned long long *) keys_out.p, n,
+			                                             g_children_of(bvh), bvh->parent);
+			LCU(cudaGetLastError());
+		}
+		if (n >= 2) {
+			/* visit[0] doubles as the result cell (refit clears the array afterwards) */
+			LCU(cudaMemsetAsync(bvh->visit, 0, sizeof(unsigned int), stream));
+			depth_kernel<<<blocks, 256, 0, stream>>>(bvh->parent, n, (int *) bvh->visit);
+			LCU(cudaGetLastError());
+			LCU(cudaMemcpyAsync(&bvh->depth, bvh->visit, sizeof(int), cudaMemcpyDeviceToHost, stream));
+		}
+		LCU(cudaStreamSynchronize(stream));
 	}
 	int rc = locate_emitter(bvh, hs->only_emitter, stream);
 	if (rc != RT_OK) return rc;
